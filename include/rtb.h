@@ -1,0 +1,325 @@
+/*
+ * rtb.h — C ABI of the B200-native path-tracing hot path ("rtb" = ray-trace-B200).
+ *
+ * This is the drop-in boundary for dariooddenino/zig-raytracing-weekend.  The reference has no
+ * FFI layer; the seam it replaces is the Zig method
+ *     Camera.render(self:*Camera, raytrace:*RayTraceState, context:Task) !void   (src/camera.zig:93-116)
+ * as invoked by RenderThread.renderFn (src/main.zig:66-68) on 8 threads spawned by startRender
+ * (src/main.zig:314-326).  The Zig host keeps scene construction (Camera options + Camera.init,
+ * the hittable list, BVHTree.init) and display; it lowers its pointer graph into the POD arrays
+ * below ONCE (rtb_scene_create) and then calls rtb_render* instead of spawning render threads.
+ *
+ * Conventions: plain pointers + sizes, no C++/torch types.  Every function returns RTB_OK (0) or
+ * a negative RtbStatus; rtb_last_error() gives a thread-local message.  Nothing throws or aborts
+ * across the boundary.  Host buffers are owned by the caller and are not retained after a
+ * synchronous call returns (async jobs: until rtb_job_wait / rtb_job_destroy).
+ *
+ * All floats are IEEE binary32.  Vectors are 3 packed floats (the reference uses @Vector(3,f32)).
+ */
+#ifndef RTB_H
+#define RTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_ABI_VERSION 1u
+
+typedef enum RtbStatus {
+    RTB_OK = 0,
+    RTB_ERR_INVALID_ARGUMENT = -1,
+    RTB_ERR_CUDA = -2,
+    RTB_ERR_NO_DEVICE = -3,
+    RTB_ERR_OUT_OF_MEMORY = -4,
+    RTB_ERR_CANCELLED = -5,
+    RTB_ERR_UNSUPPORTED = -6
+} RtbStatus;
+
+/* ------------------------------------------------------------------------------------------
+ * Scene description (host side, read once by rtb_scene_create).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Hittable variants lowered from the tagged union at src/objects.zig:39-47.
+ * LIST/TRANSLATE/ROTATE_Y/CONSTANT_MEDIUM are SURVEY §8(f) "next" rows; RoundBox is unfinished
+ * in the reference (src/objects.zig:171-192) and has no tag. */
+enum { RTB_HITTABLE_SPHERE = 0, RTB_HITTABLE_QUAD = 1 };
+
+/* Material variants, src/material.zig:11-16. */
+enum {
+    RTB_MAT_LAMBERTIAN = 0,
+    RTB_MAT_METAL = 1,
+    RTB_MAT_DIELECTRIC = 2,
+    RTB_MAT_DIFFUSE_LIGHT = 3,
+    RTB_MAT_ISOTROPIC = 4
+};
+
+/* Texture variants, src/textures.zig:10-14. */
+enum { RTB_TEX_SOLID = 0, RTB_TEX_CHECKER = 1, RTB_TEX_IMAGE = 2, RTB_TEX_NOISE = 3 };
+
+/* One `Hittable` of the world list (`world_objects.items[i]`, e.g. src/main.zig:309).  Its
+ * position in RtbSceneDesc.hittables is the "object index" reported by rtb_trace_rays.
+ *   sphere (src/objects.zig:68-75): a = center1, b = center_vec (zero unless is_moving), radius
+ *   quad   (src/objects.zig:195-204): a = q, b = u, c = v
+ * The bounding box is not carried here: the BVH nodes hold the boxes the host computed
+ * (Sphere.init / initMoving, src/objects.zig:80-92). */
+typedef struct RtbHittable {
+    uint32_t type;      /* RTB_HITTABLE_* */
+    uint32_t material;  /* index into RtbSceneDesc.materials (the reference stores Material by value) */
+    uint32_t is_moving; /* sphere only, src/objects.zig:72 */
+    float radius;       /* sphere only */
+    float a[3];
+    float b[3];
+    float c[3];
+    uint32_t reserved;
+} RtbHittable; /* 56 bytes */
+
+/* src/material.zig:32-144.
+ *   lambertian:    texture = albedo texture          (:33)
+ *   metal:         albedo, fuzz (already clamped <=1) (:58-63)
+ *   dielectric:    ir                                 (:74)
+ *   diffuse_light: texture = emit texture             (:109)
+ *   isotropic:     texture = albedo texture           (:129) */
+typedef struct RtbMaterial {
+    uint32_t type;    /* RTB_MAT_* */
+    uint32_t texture; /* index into RtbSceneDesc.textures, when the variant has one */
+    float albedo[3];
+    float fuzz;
+    float ir;
+    uint32_t reserved;
+} RtbMaterial; /* 32 bytes */
+
+/* src/textures.zig:29-124.
+ *   solid:   color                                   (:30)
+ *   checker: inv_scale (= 1/scale, :54), color = even, color2 = odd (SolidColor only, :50-51)
+ *   image:   index into RtbSceneDesc.images          (:76)
+ *   noise:   index into RtbSceneDesc.perlins, scale  (:108-109) */
+typedef struct RtbTexture {
+    uint32_t type;  /* RTB_TEX_* */
+    uint32_t index; /* image / perlin table index */
+    float scale;    /* checker: inv_scale; noise: scale */
+    float color[3];
+    float color2[3];
+    uint32_t reserved[3];
+} RtbTexture; /* 48 bytes */
+
+/* Perlin tables of one NoiseTexture instance, generated on the host by Perlin.init
+ * (src/perlin.zig:76-101) and uploaded, never regenerated on the device. */
+typedef struct RtbPerlin {
+    float ranvec[256][3];
+    uint16_t perm_x[256];
+    uint16_t perm_y[256];
+    uint16_t perm_z[256];
+} RtbPerlin;
+
+/* A decoded RGBA8 image as zstbi.Image.loadFromFile(path, 4) yields it
+ * (libs/zstbi/src/zstbi.zig:118-152; consumed by src/rtw_image.zig:51-62).
+ * Only R,G,B of each 4-byte texel are read. */
+typedef struct RtbImage {
+    uint32_t width;
+    uint32_t height;
+    uint32_t bytes_per_row;
+    uint32_t reserved;
+    const uint8_t* data;
+} RtbImage;
+
+/* One BVHNode (src/bvh.zig:106-110) with its pointers turned into indices.  Any node order is
+ * accepted; the library re-lays the tree out for the device.
+ *   leaf  >= 0: index into hittables, left = right = -1
+ *   leaf  <  0: interior, left/right index into nodes
+ * bmin/bmax = bounding_box {x,y,z}.{min,max} (src/aabb.zig:13-16). */
+typedef struct RtbBvhNode {
+    float bmin[3];
+    float bmax[3];
+    int32_t left;
+    int32_t right;
+    int32_t leaf;
+    uint32_t reserved;
+} RtbBvhNode; /* 40 bytes */
+
+typedef struct RtbSceneDesc {
+    uint32_t abi_version; /* RTB_ABI_VERSION */
+    uint32_t n_nodes;
+    uint32_t n_hittables;
+    uint32_t n_materials;
+    uint32_t n_textures;
+    uint32_t n_perlins;
+    uint32_t n_images;
+    int32_t root; /* index of BVHTree.root (src/bvh.zig:20) */
+    const RtbBvhNode* nodes;
+    const RtbHittable* hittables;
+    const RtbMaterial* materials;
+    const RtbTexture* textures;
+    const RtbPerlin* perlins;
+    const RtbImage* images;
+} RtbSceneDesc;
+
+/* ------------------------------------------------------------------------------------------
+ * Camera: the fields Camera.init derives (src/camera.zig:118-154) plus the options the hot
+ * loop reads (src/camera.zig:71-91).  The host computes them; the device only consumes them.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+    RTB_BACKGROUND_SOLID = 0, /* HEAD: return self.background           (src/camera.zig:207)     */
+    RTB_BACKGROUND_SKY = 1    /* legacy Book-1 gradient kept as a comment (src/camera.zig:204-206) */
+};
+
+typedef struct RtbCamera {
+    uint32_t image_width;
+    uint32_t image_height;
+    uint32_t samples_per_pixel;
+    uint32_t max_depth;
+    float center[3];
+    float pixel00_loc[3];
+    float pixel_delta_u[3];
+    float pixel_delta_v[3];
+    float defocus_disk_u[3];
+    float defocus_disk_v[3];
+    float defocus_angle;
+    float background[3];
+    uint32_t background_mode; /* RTB_BACKGROUND_* */
+    uint32_t reserved;
+} RtbCamera;
+
+/* ------------------------------------------------------------------------------------------
+ * Render options.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+    RTB_INTEGRATOR_MEGAKERNEL = 0, /* one persistent kernel: raygen + traversal + scatter per thread */
+    RTB_INTEGRATOR_WAVEFRONT = 1   /* raygen / extend / shade kernels over compacted ray queues      */
+};
+
+enum {
+    /* Reference order: left subtree, then right with t_max shrunk to the left hit; leaves are not
+     * box-tested (src/bvh.zig:122-136).  Bit-exact nearest-hit index against the oracle. */
+    RTB_TRAVERSAL_REFERENCE = 0,
+    /* Same tree, same intersection arithmetic, but leaves are box-tested before the primitive
+     * (conservative cull; differs from the reference only where fp rounding puts a sphere root
+     * outside its own float box). */
+    RTB_TRAVERSAL_CULL_LEAVES = 1
+};
+
+enum {
+    RTB_FLAG_COUNT_WORK = 1u << 0 /* fill RtbRenderStats.n_box_tests / n_object_tests / n_rays (slower) */
+};
+
+typedef struct RtbRenderOptions {
+    uint64_t seed;         /* Philox4x32-10 key; streams are keyed (pixel, sample, segment, block)   */
+    uint32_t sample_begin; /* first sample index (0-based); Philox uses the global sample index    */
+    uint32_t sample_count; /* number of samples to add; 0 means camera.samples_per_pixel            */
+    /* Pixel partition.  Task{thread_idx, chunk_size} (src/camera.zig:19, :94-95) maps to
+     * pixel_begin = thread_idx*chunk_size, pixel_count = chunk_size.  0/0 means the whole frame. */
+    uint32_t pixel_begin;
+    uint32_t pixel_count;
+    /* Interleaved-tile partition for multi-GPU: of the 32-pixel-wide x 4-row tiles inside the pixel
+     * range, this call renders those with tile_index % tile_world == tile_rank.  0/0 or 0/1 = all. */
+    uint32_t tile_rank;
+    uint32_t tile_world;
+    uint32_t integrator; /* RTB_INTEGRATOR_* */
+    uint32_t traversal;  /* RTB_TRAVERSAL_*  */
+    uint32_t flags;      /* RTB_FLAG_*       */
+    uint32_t samples_per_launch; /* progressive/cancel granularity; 0 = library default */
+} RtbRenderOptions;
+
+typedef struct RtbRenderStats {
+    uint64_t n_paths;        /* camera samples traced                               */
+    uint64_t n_rays;         /* ray segments (all bounces)       [RTB_FLAG_COUNT_WORK] */
+    uint64_t n_box_tests;    /* interior-node slab tests          [RTB_FLAG_COUNT_WORK] */
+    uint64_t n_object_tests; /* leaf primitive tests              [RTB_FLAG_COUNT_WORK] */
+    uint64_t n_hits;         /* accepted nearest hits (= shaded)  [RTB_FLAG_COUNT_WORK] */
+    double device_ms;        /* CUDA-event time of the render kernels on the launch stream */
+    uint32_t n_launches;     /* kernels launched by this call */
+    uint32_t reserved;
+} RtbRenderStats;
+
+/* ------------------------------------------------------------------------------------------
+ * Ray queries for the parity harness (north_star: "given identical ray batches ...").
+ * ---------------------------------------------------------------------------------------- */
+typedef struct RtbRay {
+    float origin[3];
+    float direction[3]; /* not normalised, as in the reference (src/camera.zig:176) */
+    float time;
+    float t_min; /* Interval ray_t (src/camera.zig:187): 0.001 */
+    float t_max; /*                                       +inf */
+} RtbRay; /* 36 bytes */
+
+typedef struct RtbHit {
+    int32_t object;      /* index into hittables, -1 = miss */
+    uint32_t front_face; /* HitRecord.front_face (src/objects.zig:28,34) */
+    float t;
+    float p[3];
+    float normal[3];
+    float u;
+    float v;
+    uint32_t n_box_tests;    /* interior slab tests this ray performed */
+    uint32_t n_object_tests; /* leaf primitive tests this ray performed */
+} RtbHit; /* 52 bytes */
+
+/* ------------------------------------------------------------------------------------------
+ * Entry points.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct RtbScene RtbScene; /* opaque: device copy of one scene, bound to one CUDA device */
+typedef struct RtbJob RtbJob;     /* opaque: one asynchronous render                             */
+
+uint32_t rtb_abi_version(void);
+const char* rtb_last_error(void);
+
+/* Number of CUDA devices visible; RTB_ERR_NO_DEVICE when there is none (no CPU fallback). */
+int rtb_device_count(int* count);
+
+/* Copies the scene to `device` (cudaSetDevice ordinal).  Replaces: nothing is copied in the
+ * reference — world is read in place by the worker threads (src/camera.zig:104). */
+int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene** scene_out);
+int rtb_scene_destroy(RtbScene* scene);
+
+/* Nearest hit of each ray: `world.hit(r, ray_t)` (src/camera.zig:189 → src/bvh.zig:39-41).
+ * rays/hits are HOST arrays of n elements.  traversal = RTB_TRAVERSAL_*. */
+int rtb_trace_rays(RtbScene* scene, const RtbRay* rays, uint64_t n, uint32_t traversal, RtbHit* hits_out);
+
+/* The render loop: replaces Camera.render on all threads (src/camera.zig:93-116) and
+ * SharedStateImageWriter.writeColor (src/camera.zig:54-66).
+ *   accum: HOST float[4*W*H], row-major i = y*W + x, (sum R, sum G, sum B, n) exactly like
+ *          writer.buffer; samples are ADDED to what it holds and .w is set to
+ *          sample_begin + sample_count for every pixel this call touched.
+ *   rgba:  HOST uint8[4*W*H] like writer.texture_buffer, or NULL.  Quantised from accum with
+ *          toGamma2 + truncation (src/color.zig:43-62, src/camera.zig:59-64), A = 255.
+ *   stats: optional. */
+int rtb_render(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions* options,
+               float* accum, uint8_t* rgba, RtbRenderStats* stats);
+
+/* Same, with DEVICE buffers on the scene's device and the caller's CUDA stream (cudaStream_t as
+ * void*; NULL = default stream).  Asynchronous with respect to the host unless `stats` is
+ * non-NULL (then it synchronises the stream to read the timers/counters).  Used by the
+ * multi-GPU driver so that the per-rank accumulators can be reduced in place. */
+int rtb_render_device(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions* options,
+                      float* d_accum, void* cuda_stream, RtbRenderStats* stats);
+
+/* toGamma2 + truncation over n_pixels of a DEVICE accumulation buffer into a DEVICE RGBA8 buffer.
+ * n_samples_override > 0 replaces accum.w (used after a sample-partitioned reduce). */
+int rtb_resolve_device(const float* d_accum, uint8_t* d_rgba, uint64_t n_pixels,
+                       float n_samples_override, int device, void* cuda_stream);
+
+/* Host-buffer convenience form of the resolve (copies in, resolves on the GPU, copies out). */
+int rtb_resolve(const float* accum, uint8_t* rgba, uint64_t n_pixels, float n_samples_override, int device);
+
+/* Progressive / cancellable render, preserving the GUI behaviour of the reference (progress
+ * polling: countSamples src/main.zig:470-477; STOP: stopRender :328-336; per-sample refresh of
+ * texture_buffer: src/camera.zig:57-65).  A worker thread renders `samples_per_launch` samples at
+ * a time and refreshes the caller's accum/rgba host buffers after each batch. */
+int rtb_render_async(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions* options,
+                     float* accum, uint8_t* rgba, RtbJob** job_out);
+int rtb_job_progress(RtbJob* job, uint32_t* samples_done, uint32_t* samples_total, int* running);
+int rtb_job_cancel(RtbJob* job);                      /* takes effect at the next batch boundary */
+int rtb_job_wait(RtbJob* job, RtbRenderStats* stats); /* returns the job's final status */
+int rtb_job_destroy(RtbJob* job);
+
+/* Counter-based RNG exposed for tests: Philox4x32-10 (Salmon et al., SC'11) evaluated on the
+ * device for n counters; replaces std.crypto.random.float (src/rtweekend.zig:14-16). */
+int rtb_philox_device_selftest(const uint32_t* counters4, const uint32_t* key2, uint32_t n,
+                               uint32_t* out4, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H */

@@ -1,0 +1,369 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * identical ray batches -> nearest-hit object index and front_face bit-exact; t, normal, uv within 1e-5 relative;
+  * the same Philox streams on both sides -> images agree pixel by pixel up to float association / libm ulps;
+  * different seeds -> RMSE and mean bias within the oracle's own seed-to-seed spread.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5  # stated tolerance for t / normal / uv (BASELINE.json)
+
+
+def _rays_from_camera(orc, cam, seed, n, rng):
+    size = cam.image_width * cam.image_height
+    pixels = rng.integers(0, size, n).astype(np.uint32)
+    samples = rng.integers(0, 64, n).astype(np.uint32)
+    return orc.get_rays(cam, seed, pixels, samples)
+
+
+def _random_rays(pkg, rng, n, lo, hi):
+    rays = np.zeros(n, dtype=np.dtype(pkg._ffi.RAY_DTYPE))
+    rays["origin"] = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    rays["direction"] = rng.normal(size=(n, 3)).astype(np.float32)
+    rays["time"] = rng.random(n).astype(np.float32)
+    rays["t_min"] = 0.001
+    rays["t_max"] = np.inf
+    return rays
+
+
+def _secondary_rays(pkg, orc, desc, rays, hits, seed):
+    """Scatter every hit with the oracle to get realistic incoherent bounce rays."""
+    out = []
+    for i in np.nonzero(hits["object"] >= 0)[0]:
+        ok, _, sc = orc.scatter(desc, rays[i:i + 1], hits[i:i + 1], seed, int(i), 0, 1)
+        if ok:
+            out.append(sc)
+    return np.concatenate(out) if out else rays[:0]
+
+
+def _assert_hits_equal(gpu, cpu):
+    assert np.array_equal(gpu["object"], cpu["object"]), \
+        f"nearest-hit index differs on {np.count_nonzero(gpu['object'] != cpu['object'])} rays"
+    assert np.array_equal(gpu["front_face"], cpu["front_face"])
+    # the traversal itself must be the reference's: same number of slab and primitive tests per ray
+    assert np.array_equal(gpu["n_box_tests"], cpu["n_box_tests"])
+    assert np.array_equal(gpu["n_object_tests"], cpu["n_object_tests"])
+    hit = cpu["object"] >= 0
+    # decision arithmetic is IEEE-exact on both sides: t, p, normal are bit-identical, not merely close
+    assert np.array_equal(gpu["t"][hit], cpu["t"][hit])
+    assert np.array_equal(gpu["p"][hit], cpu["p"][hit])
+    assert np.array_equal(gpu["normal"][hit], cpu["normal"][hit])
+    for k in ("u", "v"):  # acos/atan2: CUDA libm vs glibc
+        np.testing.assert_allclose(gpu[k][hit], cpu[k][hit], rtol=REL, atol=REL)
+
+
+def test_philox_device_matches_oracle(pkg, orc):
+    rng = np.random.default_rng(0)
+    ctr = rng.integers(0, 2**32, (4096, 4), dtype=np.uint64).astype(np.uint32)
+    ctr[0] = 0
+    ctr[1] = 0xFFFFFFFF
+    key = np.array([0x12345678, 0x9ABCDEF0], dtype=np.uint32)
+    got = pkg.philox_device(ctr, key)
+    want = np.stack([orc.philox(c, key) for c in ctr])
+    assert np.array_equal(got, want)
+    assert np.array_equal(pkg.philox_device(np.zeros((1, 4), np.uint32), [0, 0])[0],
+                          np.array([0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8], dtype=np.uint32))
+
+
+@pytest.fixture(scope="module")
+def book1(pkg):
+    world = pkg.World.book1()
+    return world, pkg.Scene(world)
+
+
+def test_trace_book1_camera_and_bounce_rays(pkg, orc, book1):
+    world, scene = book1
+    cam = pkg.book1_camera(400, 10, 50).init()
+    rng = np.random.default_rng(1)
+    rays = _rays_from_camera(orc, cam, 77, 20000, rng)
+    cpu = orc.trace_rays(world.desc, rays)
+    gpu = scene.trace_rays(rays)
+    _assert_hits_equal(gpu, cpu)
+    assert (cpu["object"] >= 0).mean() > 0.5
+    bounce = _secondary_rays(pkg, orc, world.desc, rays[:6000], cpu[:6000], 77)
+    assert bounce.shape[0] > 1000
+    _assert_hits_equal(scene.trace_rays(bounce), orc.trace_rays(world.desc, bounce))
+
+
+def test_trace_book1_random_and_degenerate_rays(pkg, orc, book1):
+    world, scene = book1
+    rng = np.random.default_rng(2)
+    rays = _random_rays(pkg, rng, 20000, -12, 12)
+    rays["origin"][:, 1] = np.abs(rays["origin"][:, 1]) * 0.3
+    # zero direction components: invD = +-inf, 0*inf = NaN must fall through the comparisons (aabb.zig:87-111)
+    rays["direction"][:3000, 0] = 0.0
+    rays["direction"][3000:6000, 1] = 0.0
+    rays["direction"][6000:8000, 2] = -0.0
+    rays["direction"][8000:8500] = 0.0            # the stale aabb test's zero-direction ray
+    rays["t_max"][9000:12000] = rng.uniform(0.5, 20.0, 3000).astype(np.float32)   # finite ray_t.max
+    rays["t_min"][12000:13000] = 0.0
+    # rays starting inside / on spheres (far-root branch, objects.zig:131-134)
+    d = world.desc.contents
+    for k in range(13000, 16000):
+        h = d.hittables[int(rng.integers(0, d.n_hittables))]
+        rays["origin"][k] = np.array(h.a[:]) + rng.normal(size=3) * 0.3 * h.radius
+        rays["time"][k] = 0.0
+    _assert_hits_equal(scene.trace_rays(rays), orc.trace_rays(world.desc, rays))
+
+
+def test_trace_edge_worlds(pkg, orc):
+    rng = np.random.default_rng(3)
+    spec = pkg.material_spec()
+    # single sphere: the root is a leaf (BVHTree.constructTree span == 1)
+    w1 = pkg.World.new()
+    w1.add_sphere((0, 0, -1), 0.5, spec)
+    w1.build()
+    rays = _random_rays(pkg, rng, 4000, -2, 2)
+    _assert_hits_equal(pkg.Scene(w1).trace_rays(rays), orc.trace_rays(w1.desc, rays))
+    # two and three objects incl. a moving sphere and coincident spheres (exact t ties -> DFS-earlier wins)
+    w3 = pkg.World.new()
+    w3.add_sphere((0, 0, 0), 1.0, spec)
+    w3.add_sphere((0, 0, 0), 1.0, pkg.material_spec(material=pkg.RTB_MAT_METAL))
+    w3.add_sphere((0.5, 0, 0), 0.7, spec, center2=(0.5, 0.5, 0))
+    w3.build()
+    rays = _random_rays(pkg, rng, 8000, -3, 3)
+    cpu = orc.trace_rays(w3.desc, rays)
+    _assert_hits_equal(pkg.Scene(w3).trace_rays(rays), cpu)
+    assert len(set(cpu["object"].tolist())) >= 3
+    # the UV known-answer table of objects.zig:105-107 through the whole GPU path
+    wu = pkg.World.new()
+    wu.add_sphere((0, 0, 0), 1.0, spec)
+    wu.build()
+    table = {(1, 0, 0): (0.5, 0.5), (-1, 0, 0): (0.0, 0.5), (0, 1, 0): (0.5, 1.0), (0, -1, 0): (0.5, 0.0),
+             (0, 0, 1): (0.25, 0.5), (0, 0, -1): (0.75, 0.5)}
+    rays = np.concatenate([orc.make_ray(np.array(p, np.float32) * 3, -np.array(p, np.float32)) for p in table])
+    hits = pkg.Scene(wu).trace_rays(rays)
+    for h, (p, (u, v)) in zip(hits, table.items()):
+        assert h["object"] == 0 and h["front_face"] == 1
+        if p == (-1, 0, 0):  # u wraps: atan2(-0, -1) + pi is 0 or 2pi depending on the zero's sign
+            assert min(abs(h["u"] - 0.0), abs(h["u"] - 1.0)) < 1e-6
+        else:
+            assert abs(h["u"] - u) < 1e-6
+        assert abs(h["v"] - v) < 1e-6
+    # zero rays
+    assert pkg.Scene(wu).trace_rays(rays[:0]).shape[0] == 0
+
+
+def _render_pair(pkg, orc, world, scene, cam, seed=1234, spp=None, **opt):
+    o = pkg.render_options(seed=seed, sample_count=spp or 0, flags=pkg.RTB_FLAG_COUNT_WORK, **opt)
+    g_acc, g_rgba, g_st = scene.render(cam, o)
+    c_acc, c_rgba, c_st = orc.render(world.desc, cam, o, n_threads=8)
+    return (g_acc, g_rgba, g_st), (c_acc, c_rgba, c_st)
+
+
+def _assert_same_paths(g, c, spp, max_bad_frac=2e-3):
+    (g_acc, g_rgba, g_st), (c_acc, c_rgba, c_st) = g, c
+    # same streams, same decisions -> the work counters agree exactly unless a libm ulp flipped a path
+    for k in ("n_paths", "n_rays", "n_box_tests", "n_object_tests", "n_hits"):
+        assert abs(g_st[k] - c_st[k]) <= 2e-4 * max(1, c_st[k]), (k, g_st[k], c_st[k])
+    assert np.array_equal(g_acc[:, 3], c_acc[:, 3])
+    diff = np.abs(g_acc[:, :3] - c_acc[:, :3]).max(axis=1)
+    tol = 2e-5 * spp * np.maximum(1.0, np.abs(c_acc[:, :3]).max(axis=1) / spp)
+    bad = np.count_nonzero(diff > tol)
+    assert bad <= max_bad_frac * diff.shape[0], f"{bad} of {diff.shape[0]} pixels differ beyond float association"
+    d8 = np.abs(g_rgba.astype(np.int32) - c_rgba.astype(np.int32))
+    assert np.count_nonzero(d8 > 1) <= max_bad_frac * d8.shape[0] * 4
+
+
+def test_render_book1_same_streams_as_oracle(pkg, orc, book1):
+    world, scene = book1
+    cam = pkg.book1_camera(256, 4, 50).init()
+    g, c = _render_pair(pkg, orc, world, scene, cam)
+    _assert_same_paths(g, c, 4)
+    assert g[2]["n_launches"] >= 1 and g[2]["device_ms"] > 0
+
+
+def test_render_textured_same_streams_as_oracle(pkg, orc, earthmap):
+    world = pkg.World.create(pkg.RTW_SCENE_TEXTURED, image=earthmap)
+    scene = pkg.Scene(world)
+    cam = pkg.textured_camera(192, 4, 50).init()
+    g, c = _render_pair(pkg, orc, world, scene, cam)
+    # image texels flip on acos/atan2 ulps and perlin's sin differs by ulps: allow more (still tiny) drift
+    _assert_same_paths(g, c, 4, max_bad_frac=1e-2)
+    # HEAD's Book-1 variant: checker ground + earth sphere (main.zig:257-303)
+    world2 = pkg.World.book1(checker_ground=True, earth=True, image=earthmap)
+    g, c = _render_pair(pkg, orc, world2, pkg.Scene(world2), pkg.book1_camera(160, 2, 50).init())
+    _assert_same_paths(g, c, 2, max_bad_frac=1e-2)
+
+
+def test_wavefront_equals_megakernel_bit_exact(pkg, book1, earthmap):
+    world, scene = book1
+    cam = pkg.book1_camera(200, 6, 50).init()
+    a, ra, sa = scene.render(cam, pkg.render_options(seed=5, flags=pkg.RTB_FLAG_COUNT_WORK))
+    b, rb, sb = scene.render(cam, pkg.render_options(seed=5, flags=pkg.RTB_FLAG_COUNT_WORK,
+                                                     integrator=pkg.RTB_INTEGRATOR_WAVEFRONT))
+    assert np.array_equal(a, b) and np.array_equal(ra, rb)
+    for k in ("n_paths", "n_rays", "n_box_tests", "n_object_tests", "n_hits"):
+        assert sa[k] == sb[k], k
+    wt = pkg.World.create(pkg.RTW_SCENE_TEXTURED, image=earthmap)
+    st = pkg.Scene(wt)
+    camt = pkg.textured_camera(160, 3, 12).init()
+    a, _, _ = st.render(camt, pkg.render_options(seed=6))
+    b, _, _ = st.render(camt, pkg.render_options(seed=6, integrator=pkg.RTB_INTEGRATOR_WAVEFRONT))
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("integrator", [0, 1])
+def test_sample_ranges_and_partitions_compose_bit_exact(pkg, book1, integrator):
+    world, scene = book1
+    cam = pkg.book1_camera(176, 8, 50).init()   # 176 x 99: ragged against the 32 x 8 tiles
+    full, _, _ = scene.render(cam, pkg.render_options(seed=9, integrator=integrator))
+    # progressive: 0..3 then 3..8 into the same buffer (resumable accumulation, camera.zig:54-56)
+    acc, _, _ = scene.render(cam, pkg.render_options(seed=9, sample_begin=0, sample_count=3, integrator=integrator))
+    acc, _, _ = scene.render(cam, pkg.render_options(seed=9, sample_begin=3, sample_count=5, integrator=integrator),
+                             accum=acc)
+    assert np.array_equal(acc, full)
+    # samples_per_launch batching does not change the result
+    b, _, _ = scene.render(cam, pkg.render_options(seed=9, samples_per_launch=3, integrator=integrator))
+    assert np.array_equal(b, full)
+    # interleaved tile partition (multi-GPU mode A): 3 ranks write disjoint pixels; sum of buffers == full frame
+    n = cam.image_width * cam.image_height
+    parts = []
+    for r in range(3):
+        z = np.zeros((n, 4), np.float32)
+        z, _, _ = scene.render(cam, pkg.render_options(seed=9, tile_rank=r, tile_world=3, integrator=integrator),
+                               accum=z)
+        parts.append(z)
+    owners = sum((p[:, 3] > 0).astype(int) for p in parts)
+    assert (owners == 1).all()
+    assert np.array_equal(sum(parts), full)
+    # Task{thread_idx, chunk_size} strips (camera.zig:94-95): 8 strips of size/8 pixels (+ remainder)
+    acc2 = np.zeros((n, 4), np.float32)
+    chunk = n // 8
+    for t in range(8):
+        cnt = chunk if t < 7 else n - 7 * chunk
+        acc2, _, _ = scene.render(cam, pkg.render_options(seed=9, pixel_begin=t * chunk, pixel_count=cnt,
+                                                          integrator=integrator), accum=acc2)
+    assert np.array_equal(acc2, full)
+
+
+def test_depth_limits_and_backgrounds(pkg, orc, book1):
+    world, scene = book1
+    for depth in (0, 1, 2):
+        c = pkg.book1_camera(96, 2, depth)
+        c.background_mode = pkg.RTB_BACKGROUND_SOLID
+        c.background = (0.3, 0.6, 0.9)
+        cam = c.init()
+        g, cc = _render_pair(pkg, orc, world, scene, cam)
+        _assert_same_paths(g, cc, 2)
+        if depth == 0:
+            assert (g[0][:, :3] == 0).all() and (g[0][:, 3] == 2).all()
+
+
+def test_resolve_matches_oracle(pkg, orc):
+    rng = np.random.default_rng(4)
+    acc = np.zeros((4096, 4), np.float32)
+    acc[:, :3] = rng.random((4096, 3)).astype(np.float32) * 40
+    acc[:, 3] = rng.integers(1, 40, 4096)
+    acc[0, :3] = 0
+    acc[1, :3] = 1e9          # clamp to 0.999 -> 255
+    acc[2, :3] = -1.0         # sqrt(<0) = NaN -> 0 (reference: undefined)
+    acc[3, :3] = np.nan
+    assert np.array_equal(pkg.resolve(acc), orc.resolve(acc))
+    assert np.array_equal(pkg.resolve(acc, 7.0), orc.resolve(acc, 7.0))
+    assert pkg.resolve(acc)[1].tolist() == [255, 255, 255, 255]
+
+
+def test_camera_render_drop_in(pkg, book1):
+    """rtw_camera_render = the call that replaces startRender's 8 threads (main.zig:314-326)."""
+    world, scene = book1
+    c = pkg.book1_camera(128, 3, 50)
+    cam = c.init()
+    buf, tex = pkg.new_writer(cam)
+    buf[:] = 123.0  # scrub must reset it
+    st = pkg.RtbRenderStats()
+    o = c.options()
+    ro = pkg.render_options(seed=11)
+    rc = pkg._ffi.rtw().rtw_camera_render(scene._h, C.byref(o), C.byref(ro), 1, buf.ctypes.data, tex.ctypes.data,
+                                          C.byref(st))
+    assert rc == 0
+    ref, ref_rgba, _ = scene.render(cam, pkg.render_options(seed=11))
+    assert np.array_equal(buf, ref) and np.array_equal(tex, ref_rgba)
+    assert (tex[:, 3] == 255).all() and (buf[:, 3] == 3).all()
+
+
+def test_async_progress_and_cancel(pkg, book1):
+    world, scene = book1
+    cam = pkg.book1_camera(320, 64, 50).init()
+    acc, rgba = pkg.new_writer(cam)
+    job = scene.render_async(cam, pkg.render_options(seed=3, samples_per_launch=2), acc, rgba)
+    seen = 0
+    t0 = time.time()
+    while time.time() - t0 < 60:
+        done, total, running = job.progress()
+        assert total == 64
+        seen = max(seen, done)
+        if done >= 6 or not running:
+            break
+        time.sleep(0.002)
+    job.cancel()
+    rc, st = job.wait()
+    done, total, running = job.progress()
+    assert not running
+    if rc == pkg.RTB_ERR_CANCELLED:
+        assert 0 < done < 64
+    else:
+        assert rc == 0 and done == 64
+    # the buffers hold exactly `done` samples, like writer.buffer after STOP (main.zig:328-336)
+    assert (acc[:, 3] == done).all()
+    ref, _, _ = scene.render(cam, pkg.render_options(seed=3, sample_count=done))
+    assert np.array_equal(acc, ref)
+    job.destroy()
+
+
+def test_statistical_parity_different_seeds(pkg, orc, book1):
+    """North-star image bar: RMSE(GPU,CPU) <= 1.25 RMSE_self, |mean bias| <= max(0.002, 3 RMSE_self/sqrt(WH))."""
+    world, scene = book1
+    spp = 32
+    cam = pkg.book1_camera(240, spp, 50).init()
+    c1 = orc.render(world.desc, cam, pkg.render_options(seed=4321), want_rgba=False)[0]
+    c2 = orc.render(world.desc, cam, pkg.render_options(seed=8765), want_rgba=False)[0]
+    g = scene.render(cam, pkg.render_options(seed=1234))[0]
+    m = lambda a: a[:, :3] / a[:, 3:4]
+    rmse_self = np.sqrt(((m(c1) - m(c2)) ** 2).mean(axis=0))
+    rmse = np.sqrt(((m(g) - m(c1)) ** 2).mean(axis=0))
+    bias = np.abs((m(g) - m(c1)).mean(axis=0))
+    assert (rmse <= 1.25 * rmse_self).all(), (rmse, rmse_self)
+    assert (bias <= np.maximum(0.002, 3 * rmse_self / np.sqrt(g.shape[0]))).all(), (bias, rmse_self)
+
+
+def test_error_paths(pkg, book1):
+    world, scene = book1
+    cam = pkg.book1_camera(64, 1, 4).init()
+    with pytest.raises(pkg.RtbError) as e:
+        scene.render(cam, pkg.render_options(tile_rank=2, tile_world=2))
+    assert e.value.code == pkg.RTB_ERR_INVALID_ARGUMENT
+    with pytest.raises(pkg.RtbError):
+        scene.render(cam, pkg.render_options(pixel_begin=10, pixel_count=10**7))
+    with pytest.raises(pkg.RtbError) as e:
+        scene.render(cam, pkg.render_options(traversal=7))
+    assert e.value.code == pkg.RTB_ERR_UNSUPPORTED
+    with pytest.raises(pkg.RtbError):
+        pkg.Scene(world, device=99)
+
+
+def test_full_size_properties_config2(pkg, book1):
+    """BASELINE config 2 frame size (1200x675), reduced spp: size-independent properties."""
+    world, scene = book1
+    cam = pkg.book1_camera(1200, 8, 50).init()
+    assert cam.image_height == 675
+    a, rgba, st = scene.render(cam, pkg.render_options(seed=1234, flags=pkg.RTB_FLAG_COUNT_WORK))
+    assert st["n_paths"] == 1200 * 675 * 8
+    assert np.isfinite(a).all() and (a[:, :3] >= 0).all() and (a[:, 3] == 8).all()
+    # energy: no emitters and sky radiance <= 1 -> every sample <= 1
+    assert (a[:, :3] <= 8.0 + 1e-3).all()
+    # idempotence / determinism: the same call gives the same bits
+    b, _, _ = scene.render(cam, pkg.render_options(seed=1234))
+    assert np.array_equal(a, b)
+    # linearity in samples: 8 spp == 5 spp + 3 spp
+    c, _, _ = scene.render(cam, pkg.render_options(seed=1234, sample_count=5))
+    c, _, _ = scene.render(cam, pkg.render_options(seed=1234, sample_begin=5, sample_count=3), accum=c)
+    assert np.array_equal(a, c)
+    assert 2.0 < st["n_rays"] / st["n_paths"] < 6.0

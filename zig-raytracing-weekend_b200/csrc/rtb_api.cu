@@ -1,0 +1,684 @@
+// rtb_api.cu — implementation of the C ABI declared in include/rtb.h.
+//
+// Host-side only: validates and re-lays out the scene for the device (threaded pre-order BVH,
+// packed materials/textures), owns device memory behind the opaque handles, launches the kernels
+// of rtb_kernels.cu and maps CUDA errors to RtbStatus.  There is NO CPU fallback: without a CUDA
+// device every compute entry point fails with RTB_ERR_NO_DEVICE.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rtb_kernels.cuh"
+#include "rtb_wavefront.cuh"
+
+using namespace rtb;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    const int code = (e == cudaErrorMemoryAllocation) ? RTB_ERR_OUT_OF_MEMORY
+                     : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RTB_ERR_NO_DEVICE
+                                                                                   : RTB_ERR_CUDA;
+    return fail(code, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+#define RTB_CUDA(call)                                            \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);     \
+    } while (0)
+
+// ------------------------------------------------------------------ handles
+struct RtbScene {
+    int device = 0;
+    DevScene dev{};
+    uint32_t max_depth = 0;  // tree depth (diagnostics)
+    std::vector<void*> allocations;
+    bool nodes_fit_smem = false;
+    unsigned long long* d_counters = nullptr;
+    WavefrontState* wavefront = nullptr;
+    std::mutex mutex;  // serialises renders on one scene (counters / wavefront queues are shared)
+};
+
+struct RtbJob {
+    std::thread worker;
+    std::atomic<uint32_t> samples_done{0};
+    uint32_t samples_total = 0;
+    std::atomic<int> running{1};
+    std::atomic<int> cancel{0};
+    int status = RTB_OK;
+    std::string error;
+    RtbRenderStats stats{};
+};
+
+extern "C" uint32_t rtb_abi_version(void) { return RTB_ABI_VERSION; }
+extern "C" const char* rtb_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int rtb_device_count(int* count) {
+    if (!count) return fail(RTB_ERR_INVALID_ARGUMENT, "rtb_device_count: count is NULL");
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(RTB_ERR_NO_DEVICE, "no CUDA device visible (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    }
+    *count = n;
+    return RTB_OK;
+}
+
+// ------------------------------------------------------------------ scene lowering
+template <class T>
+static int upload(RtbScene* sc, const std::vector<T>& host, const T** dev_out) {
+    *dev_out = nullptr;
+    if (host.empty()) return RTB_OK;
+    void* d = nullptr;
+    RTB_CUDA(cudaMalloc(&d, host.size() * sizeof(T)));
+    sc->allocations.push_back(d);
+    RTB_CUDA(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dev_out = static_cast<const T*>(d);
+    return RTB_OK;
+}
+
+static inline float4 mkf4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
+static inline float bits(uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+// Quad.init's derived fields (src/objects.zig:206-211), evaluated unfused in f32 on the host.
+static DevQuad make_quad(const RtbHittable& h) {
+    const float q[3] = {h.a[0], h.a[1], h.a[2]}, u[3] = {h.b[0], h.b[1], h.b[2]}, v[3] = {h.c[0], h.c[1], h.c[2]};
+    const float n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+    const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    const float normal[3] = {n[0] / len, n[1] / len, n[2] / len};
+    const float d = normal[0] * q[0] + normal[1] * q[1] + normal[2] * q[2];
+    const float nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    DevQuad dq;
+    dq.q_d = mkf4(q[0], q[1], q[2], d);
+    dq.u = mkf4(u[0], u[1], u[2], 0);
+    dq.v = mkf4(v[0], v[1], v[2], 0);
+    dq.normal = mkf4(normal[0], normal[1], normal[2], 0);
+    dq.w = mkf4(n[0] / nn, n[1] / nn, n[2] / nn, 0);
+    return dq;
+}
+
+static int validate_desc(const RtbSceneDesc* d) {
+    if (!d) return fail(RTB_ERR_INVALID_ARGUMENT, "scene desc is NULL");
+    if (d->abi_version != RTB_ABI_VERSION)
+        return fail(RTB_ERR_INVALID_ARGUMENT, "abi_version %u != %u", d->abi_version, RTB_ABI_VERSION);
+    if ((d->n_nodes && !d->nodes) || (d->n_hittables && !d->hittables) || (d->n_materials && !d->materials) ||
+        (d->n_textures && !d->textures) || (d->n_perlins && !d->perlins) || (d->n_images && !d->images))
+        return fail(RTB_ERR_INVALID_ARGUMENT, "scene desc has a NULL array with a non-zero count");
+    if (d->n_nodes > RTB_META_INDEX_MASK || d->n_hittables > RTB_META_INDEX_MASK)
+        return fail(RTB_ERR_INVALID_ARGUMENT, "scene too large (2^30 nodes/objects max)");
+    if (d->n_nodes && (d->root < 0 || (uint32_t)d->root >= d->n_nodes))
+        return fail(RTB_ERR_INVALID_ARGUMENT, "root %d out of range", d->root);
+    for (uint32_t i = 0; i < d->n_hittables; ++i) {
+        const RtbHittable& h = d->hittables[i];
+        if (h.type != RTB_HITTABLE_SPHERE && h.type != RTB_HITTABLE_QUAD)
+            return fail(RTB_ERR_UNSUPPORTED, "hittable %u: unsupported type %u", i, h.type);
+        if (h.material >= d->n_materials) return fail(RTB_ERR_INVALID_ARGUMENT, "hittable %u: material out of range", i);
+    }
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const RtbMaterial& m = d->materials[i];
+        if (m.type > RTB_MAT_ISOTROPIC) return fail(RTB_ERR_UNSUPPORTED, "material %u: unsupported type %u", i, m.type);
+        const bool has_tex = m.type == RTB_MAT_LAMBERTIAN || m.type == RTB_MAT_DIFFUSE_LIGHT || m.type == RTB_MAT_ISOTROPIC;
+        if (has_tex && m.texture >= d->n_textures)
+            return fail(RTB_ERR_INVALID_ARGUMENT, "material %u: texture out of range", i);
+    }
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const RtbTexture& t = d->textures[i];
+        if (t.type > RTB_TEX_NOISE) return fail(RTB_ERR_UNSUPPORTED, "texture %u: unsupported type %u", i, t.type);
+        if (t.type == RTB_TEX_IMAGE && t.index >= d->n_images)
+            return fail(RTB_ERR_INVALID_ARGUMENT, "texture %u: image out of range", i);
+        if (t.type == RTB_TEX_NOISE && t.index >= d->n_perlins)
+            return fail(RTB_ERR_INVALID_ARGUMENT, "texture %u: perlin table out of range", i);
+    }
+    for (uint32_t i = 0; i < d->n_images; ++i) {
+        const RtbImage& im = d->images[i];
+        if (im.height && im.width && (!im.data || im.bytes_per_row < im.width * 4u))
+            return fail(RTB_ERR_INVALID_ARGUMENT, "image %u: bad data/stride", i);
+    }
+    return RTB_OK;
+}
+
+// Pointer graph -> threaded pre-order array.  Iterative (no recursion: the caller's tree may be
+// arbitrarily deep).  Pass 1 computes subtree sizes in post-order, pass 2 assigns pre-order slots:
+// slot(left) = slot + 1, slot(right) = slot + 1 + size(left), skip = slot + size(self).
+static int build_threaded(const RtbSceneDesc* d, std::vector<float4>& out, std::vector<DevQuad>& quads,
+                          uint32_t* depth_out) {
+    out.clear();
+    *depth_out = 0;
+    if (d->n_nodes == 0) return RTB_OK;
+    const uint32_t n = d->n_nodes;
+    std::vector<uint32_t> size(n, 0);
+    std::vector<uint8_t> state(n, 0);  // 0 = unseen, 1 = expanded, 2 = sized
+    std::vector<int32_t> stack;
+    stack.push_back(d->root);
+    uint32_t visited = 0;
+    while (!stack.empty()) {
+        const int32_t i = stack.back();
+        const RtbBvhNode& nd = d->nodes[i];
+        if (nd.leaf >= 0) {
+            if ((uint32_t)nd.leaf >= d->n_hittables) return fail(RTB_ERR_INVALID_ARGUMENT, "node %d: leaf out of range", i);
+            if (state[i] != 0) return fail(RTB_ERR_INVALID_ARGUMENT, "node %d reached twice (not a tree)", i);
+            state[i] = 2;
+            size[i] = 1;
+            ++visited;
+            stack.pop_back();
+            continue;
+        }
+        if (nd.left < 0 || nd.right < 0 || (uint32_t)nd.left >= n || (uint32_t)nd.right >= n)
+            return fail(RTB_ERR_INVALID_ARGUMENT, "node %d: child out of range", i);
+        if (state[i] == 0) {
+            state[i] = 1;
+            ++visited;
+            if (state[nd.left] != 0 || state[nd.right] != 0 || nd.left == nd.right)
+                return fail(RTB_ERR_INVALID_ARGUMENT, "node %d: child reached twice (not a tree)", i);
+            stack.push_back(nd.right);
+            stack.push_back(nd.left);
+        } else {
+            size[i] = 1 + size[nd.left] + size[nd.right];
+            state[i] = 2;
+            stack.pop_back();
+        }
+    }
+    const uint32_t total = size[d->root];
+    out.resize(2 * (size_t)total);
+    struct Item {
+        int32_t node;
+        uint32_t slot;
+        uint32_t depth;
+    };
+    std::vector<Item> work;
+    work.push_back({d->root, 0u, 1u});
+    while (!work.empty()) {
+        const Item it = work.back();
+        work.pop_back();
+        const RtbBvhNode& nd = d->nodes[it.node];
+        if (it.depth > *depth_out) *depth_out = it.depth;
+        if (nd.leaf >= 0) {
+            const RtbHittable& h = d->hittables[nd.leaf];
+            if (h.type == RTB_HITTABLE_SPHERE) {
+                const uint32_t kind = h.is_moving ? KIND_MOVING_SPHERE : KIND_SPHERE;
+                out[2 * (size_t)it.slot] = mkf4(h.a[0], h.a[1], h.a[2], bits((kind << 30) | (uint32_t)nd.leaf));
+                out[2 * (size_t)it.slot + 1] = mkf4(h.b[0], h.b[1], h.b[2], h.radius);
+            } else {
+                out[2 * (size_t)it.slot] = mkf4(0, 0, 0, bits((KIND_QUAD << 30) | (uint32_t)nd.leaf));
+                out[2 * (size_t)it.slot + 1] = mkf4(0, 0, 0, bits((uint32_t)quads.size()));
+                quads.push_back(make_quad(h));
+            }
+        } else {
+            const uint32_t skip = it.slot + size[it.node];
+            out[2 * (size_t)it.slot] = mkf4(nd.bmin[0], nd.bmin[1], nd.bmin[2], bits((KIND_INTERIOR << 30) | skip));
+            out[2 * (size_t)it.slot + 1] = mkf4(nd.bmax[0], nd.bmax[1], nd.bmax[2], 0.0f);
+            work.push_back({nd.right, it.slot + 1u + size[nd.left], it.depth + 1u});
+            work.push_back({nd.left, it.slot + 1u, it.depth + 1u});
+        }
+    }
+    (void)visited;
+    return RTB_OK;
+}
+
+static void scene_free(RtbScene* sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    if (sc->wavefront) wavefront_destroy(sc->wavefront);
+    for (void* p : sc->allocations) cudaFree(p);
+    delete sc;
+}
+
+extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene** scene_out) {
+    if (!scene_out) return fail(RTB_ERR_INVALID_ARGUMENT, "scene_out is NULL");
+    *scene_out = nullptr;
+    int rc = validate_desc(desc);
+    if (rc != RTB_OK) return rc;
+    int ndev = 0;
+    rc = rtb_device_count(&ndev);
+    if (rc != RTB_OK) return rc;
+    if (device < 0 || device >= ndev) return fail(RTB_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, ndev - 1);
+    RTB_CUDA(cudaSetDevice(device));
+
+    std::vector<float4> nodes;
+    std::vector<DevQuad> quads;
+    uint32_t depth = 0;
+    rc = build_threaded(desc, nodes, quads, &depth);
+    if (rc != RTB_OK) return rc;
+
+    RtbScene* sc = new (std::nothrow) RtbScene();
+    if (!sc) return fail(RTB_ERR_OUT_OF_MEMORY, "host allocation failed");
+    sc->device = device;
+    sc->max_depth = depth;
+
+    std::vector<uint32_t> obj_mat(desc->n_hittables);
+    for (uint32_t i = 0; i < desc->n_hittables; ++i) obj_mat[i] = desc->hittables[i].material;
+
+    std::vector<float4> mats(2 * (size_t)desc->n_materials);
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const RtbMaterial& m = desc->materials[i];
+        const bool has_tex = m.type == RTB_MAT_LAMBERTIAN || m.type == RTB_MAT_DIFFUSE_LIGHT || m.type == RTB_MAT_ISOTROPIC;
+        uint32_t tex_type = RTB_TEX_SOLID;
+        float rgb[3] = {m.albedo[0], m.albedo[1], m.albedo[2]};
+        if (has_tex) {
+            const RtbTexture& t = desc->textures[m.texture];
+            tex_type = t.type;
+            if (t.type == RTB_TEX_SOLID) std::memcpy(rgb, t.color, sizeof(rgb));  // inline the solid colour
+        }
+        mats[2 * (size_t)i] = mkf4(bits(m.type | (tex_type << 8)), bits(has_tex ? m.texture : 0u), m.fuzz, m.ir);
+        mats[2 * (size_t)i + 1] = mkf4(rgb[0], rgb[1], rgb[2], 0.0f);
+    }
+    std::vector<float4> texs(3 * (size_t)desc->n_textures);
+    for (uint32_t i = 0; i < desc->n_textures; ++i) {
+        const RtbTexture& t = desc->textures[i];
+        texs[3 * (size_t)i] = mkf4(bits(t.type), bits(t.index), t.scale, 0.0f);
+        texs[3 * (size_t)i + 1] = mkf4(t.color[0], t.color[1], t.color[2], 0.0f);
+        texs[3 * (size_t)i + 2] = mkf4(t.color2[0], t.color2[1], t.color2[2], 0.0f);
+    }
+    std::vector<DevPerlin> perlins(desc->n_perlins);
+    for (uint32_t i = 0; i < desc->n_perlins; ++i) {
+        const RtbPerlin& p = desc->perlins[i];
+        for (int k = 0; k < 256; ++k) {
+            perlins[i].ranvec[k] = mkf4(p.ranvec[k][0], p.ranvec[k][1], p.ranvec[k][2], 0.0f);
+            perlins[i].perm_x[k] = (uint8_t)(p.perm_x[k] & 255u);
+            perlins[i].perm_y[k] = (uint8_t)(p.perm_y[k] & 255u);
+            perlins[i].perm_z[k] = (uint8_t)(p.perm_z[k] & 255u);
+        }
+    }
+    std::vector<DevImage> images(desc->n_images);
+    for (uint32_t i = 0; i < desc->n_images && rc == RTB_OK; ++i) {
+        const RtbImage& im = desc->images[i];
+        images[i].width = im.width;
+        images[i].height = im.height;
+        images[i].texels = nullptr;
+        if (im.width && im.height) {
+            std::vector<uchar4> tight((size_t)im.width * im.height);
+            for (uint32_t y = 0; y < im.height; ++y)
+                std::memcpy(&tight[(size_t)y * im.width], im.data + (size_t)y * im.bytes_per_row, (size_t)im.width * 4);
+            rc = upload(sc, tight, &images[i].texels);
+        }
+    }
+    if (rc == RTB_OK) rc = upload(sc, nodes, &sc->dev.nodes);
+    if (rc == RTB_OK) rc = upload(sc, obj_mat, &sc->dev.object_material);
+    if (rc == RTB_OK) rc = upload(sc, mats, &sc->dev.materials);
+    if (rc == RTB_OK) rc = upload(sc, texs, &sc->dev.textures);
+    if (rc == RTB_OK) rc = upload(sc, perlins, &sc->dev.perlins);
+    if (rc == RTB_OK) rc = upload(sc, images, &sc->dev.images);
+    if (rc == RTB_OK) rc = upload(sc, quads, &sc->dev.quads);
+    if (rc == RTB_OK) {
+        void* c = nullptr;
+        cudaError_t e = cudaMalloc(&c, 4 * sizeof(unsigned long long));
+        if (e != cudaSuccess)
+            rc = cuda_fail(e, "cudaMalloc(counters)");
+        else {
+            sc->allocations.push_back(c);
+            sc->d_counters = static_cast<unsigned long long*>(c);
+        }
+    }
+    if (rc != RTB_OK) {
+        scene_free(sc);
+        return rc;
+    }
+    sc->dev.n_nodes = (uint32_t)(nodes.size() / 2);
+    sc->dev.n_objects = desc->n_hittables;
+    sc->dev.has_quads = quads.empty() ? 0u : 1u;
+    sc->nodes_fit_smem = sc->dev.n_nodes > 0 && (size_t)sc->dev.n_nodes * 32u <= megakernel_max_smem_nodes_bytes();
+    *scene_out = sc;
+    return RTB_OK;
+}
+
+extern "C" int rtb_scene_destroy(RtbScene* scene) {
+    if (!scene) return RTB_OK;
+    scene_free(scene);
+    return RTB_OK;
+}
+
+// ------------------------------------------------------------------ ray queries
+extern "C" int rtb_trace_rays(RtbScene* scene, const RtbRay* rays, uint64_t n, uint32_t traversal, RtbHit* hits_out) {
+    if (!scene) return fail(RTB_ERR_INVALID_ARGUMENT, "scene is NULL");
+    if (n && (!rays || !hits_out)) return fail(RTB_ERR_INVALID_ARGUMENT, "rays/hits_out is NULL");
+    if (traversal != RTB_TRAVERSAL_REFERENCE) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", traversal);
+    if (n == 0) return RTB_OK;
+    std::lock_guard<std::mutex> lock(scene->mutex);
+    RTB_CUDA(cudaSetDevice(scene->device));
+    RtbRay* d_rays = nullptr;
+    RtbHit* d_hits = nullptr;
+    RTB_CUDA(cudaMalloc(&d_rays, n * sizeof(RtbRay)));
+    cudaError_t e = cudaMalloc(&d_hits, n * sizeof(RtbHit));
+    if (e == cudaSuccess) e = cudaMemcpy(d_rays, rays, n * sizeof(RtbRay), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_trace(scene->dev, d_rays, n, d_hits, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(hits_out, d_hits, n * sizeof(RtbHit), cudaMemcpyDeviceToHost);
+    cudaFree(d_rays);
+    cudaFree(d_hits);
+    if (e != cudaSuccess) return cuda_fail(e, "rtb_trace_rays");
+    return RTB_OK;
+}
+
+// ------------------------------------------------------------------ render
+static DevCamera lower_camera(const RtbCamera* c) {
+    DevCamera d;
+    d.center = make_float3(c->center[0], c->center[1], c->center[2]);
+    d.pixel00 = make_float3(c->pixel00_loc[0], c->pixel00_loc[1], c->pixel00_loc[2]);
+    d.du = make_float3(c->pixel_delta_u[0], c->pixel_delta_u[1], c->pixel_delta_u[2]);
+    d.dv = make_float3(c->pixel_delta_v[0], c->pixel_delta_v[1], c->pixel_delta_v[2]);
+    d.ddu = make_float3(c->defocus_disk_u[0], c->defocus_disk_u[1], c->defocus_disk_u[2]);
+    d.ddv = make_float3(c->defocus_disk_v[0], c->defocus_disk_v[1], c->defocus_disk_v[2]);
+    d.background = make_float3(c->background[0], c->background[1], c->background[2]);
+    d.defocus_angle = c->defocus_angle;
+    d.width = c->image_width;
+    d.height = c->image_height;
+    d.max_depth = c->max_depth;
+    d.background_mode = c->background_mode;
+    return d;
+}
+
+static int check_render_args(RtbScene* scene, const RtbCamera* cam, const RtbRenderOptions* opt) {
+    if (!scene || !cam || !opt) return fail(RTB_ERR_INVALID_ARGUMENT, "scene/camera/options is NULL");
+    if (cam->image_width == 0 || cam->image_height == 0) return fail(RTB_ERR_INVALID_ARGUMENT, "empty image");
+    const uint64_t size = (uint64_t)cam->image_width * cam->image_height;
+    if (size > 0xffffffffull) return fail(RTB_ERR_INVALID_ARGUMENT, "image too large");
+    if ((uint64_t)opt->pixel_begin + opt->pixel_count > size) return fail(RTB_ERR_INVALID_ARGUMENT, "pixel range out of bounds");
+    if (opt->tile_world > 0 && opt->tile_rank >= opt->tile_world) return fail(RTB_ERR_INVALID_ARGUMENT, "tile_rank >= tile_world");
+    if (opt->integrator != RTB_INTEGRATOR_MEGAKERNEL && opt->integrator != RTB_INTEGRATOR_WAVEFRONT)
+        return fail(RTB_ERR_INVALID_ARGUMENT, "unknown integrator %u", opt->integrator);
+    if (opt->traversal != RTB_TRAVERSAL_REFERENCE) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", opt->traversal);
+    if (cam->background_mode > RTB_BACKGROUND_SKY) return fail(RTB_ERR_INVALID_ARGUMENT, "unknown background mode");
+    return RTB_OK;
+}
+
+// Core: enqueue the kernels for samples [begin, begin+count) on `stream`.  Caller holds the lock.
+static int render_enqueue(RtbScene* scene, const RtbCamera* cam, const RtbRenderOptions* opt, uint32_t begin,
+                          uint32_t count, float* d_accum, cudaStream_t stream, LaunchInfo* info) {
+    RenderParams p{};
+    p.scene = scene->dev;
+    p.cam = lower_camera(cam);
+    p.accum = reinterpret_cast<float4*>(d_accum);
+    p.seed = make_uint2((uint32_t)opt->seed, (uint32_t)(opt->seed >> 32));
+    p.sample_begin = begin;
+    p.sample_count = count;
+    const uint32_t size = cam->image_width * cam->image_height;
+    p.pixel_begin = opt->pixel_begin;
+    p.pixel_end = (opt->pixel_begin == 0 && opt->pixel_count == 0) ? size : opt->pixel_begin + opt->pixel_count;
+    p.tile_rank = opt->tile_rank;
+    p.tile_world = opt->tile_world ? opt->tile_world : 1u;
+    const bool count_work = (opt->flags & RTB_FLAG_COUNT_WORK) != 0;
+    p.counters = count_work ? scene->d_counters : nullptr;
+    if (opt->integrator == RTB_INTEGRATOR_WAVEFRONT) {
+        if (!scene->wavefront) {
+            scene->wavefront = wavefront_create();
+            if (!scene->wavefront) return fail(RTB_ERR_OUT_OF_MEMORY, "wavefront state allocation failed");
+        }
+        const cudaError_t e = wavefront_render(scene->wavefront, p, count_work, stream, info);
+        if (e != cudaSuccess) return cuda_fail(e, "wavefront_render");
+        return RTB_OK;
+    }
+    const cudaError_t e = launch_megakernel(p, scene->nodes_fit_smem, count_work, stream, info);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_megakernel");
+    return RTB_OK;
+}
+
+static int render_device_locked(RtbScene* scene, const RtbCamera* cam, const RtbRenderOptions* opt, float* d_accum,
+                                cudaStream_t stream, RtbRenderStats* stats) {
+    const uint32_t total = opt->sample_count ? opt->sample_count : cam->samples_per_pixel;
+    const uint32_t per_launch = opt->samples_per_launch ? opt->samples_per_launch : total;
+    const bool count_work = (opt->flags & RTB_FLAG_COUNT_WORK) != 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) {
+        RTB_CUDA(cudaEventCreate(&ev0));
+        RTB_CUDA(cudaEventCreate(&ev1));
+        if (count_work) RTB_CUDA(cudaMemsetAsync(scene->d_counters, 0, 4 * sizeof(unsigned long long), stream));
+        RTB_CUDA(cudaEventRecord(ev0, stream));
+    }
+    LaunchInfo info;
+    int rc = RTB_OK;
+    for (uint32_t done = 0; done < total && rc == RTB_OK;) {
+        const uint32_t n = (total - done < per_launch) ? total - done : per_launch;
+        rc = render_enqueue(scene, cam, opt, opt->sample_begin + done, n, d_accum, stream, &info);
+        done += n;
+    }
+    if (stats) {
+        if (rc == RTB_OK) {
+            cudaError_t e = cudaEventRecord(ev1, stream);
+            if (e == cudaSuccess) e = cudaEventSynchronize(ev1);
+            float ms = 0;
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev0, ev1);
+            std::memset(stats, 0, sizeof(*stats));
+            stats->device_ms = ms;
+            stats->n_launches = info.n_launches;
+            const uint32_t size = cam->image_width * cam->image_height;
+            const uint64_t npx = (opt->pixel_begin == 0 && opt->pixel_count == 0) ? size : opt->pixel_count;
+            stats->n_paths = npx * total;  // exact when tile_world <= 1
+            if (e == cudaSuccess && count_work) {
+                unsigned long long c[4];
+                e = cudaMemcpy(c, scene->d_counters, sizeof(c), cudaMemcpyDeviceToHost);
+                stats->n_rays = c[0];
+                stats->n_box_tests = c[1];
+                stats->n_object_tests = c[2];
+                stats->n_hits = c[3];
+            }
+            if (e != cudaSuccess) rc = cuda_fail(e, "render stats");
+        }
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return rc;
+}
+
+extern "C" int rtb_render_device(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions* options,
+                                 float* d_accum, void* cuda_stream, RtbRenderStats* stats) {
+    int rc = check_render_args(scene, camera, options);
+    if (rc != RTB_OK) return rc;
+    if (!d_accum) return fail(RTB_ERR_INVALID_ARGUMENT, "d_accum is NULL");
+    std::lock_guard<std::mutex> lock(scene->mutex);
+    RTB_CUDA(cudaSetDevice(scene->device));
+    return render_device_locked(scene, camera, options, d_accum, static_cast<cudaStream_t>(cuda_stream), stats);
+}
+
+extern "C" int rtb_resolve_device(const float* d_accum, uint8_t* d_rgba, uint64_t n_pixels, float n_samples_override,
+                                  int device, void* cuda_stream) {
+    if (n_pixels && (!d_accum || !d_rgba)) return fail(RTB_ERR_INVALID_ARGUMENT, "d_accum/d_rgba is NULL");
+    RTB_CUDA(cudaSetDevice(device));
+    const cudaError_t e = launch_resolve(reinterpret_cast<const float4*>(d_accum), reinterpret_cast<uchar4*>(d_rgba),
+                                         n_pixels, n_samples_override, static_cast<cudaStream_t>(cuda_stream));
+    if (e != cudaSuccess) return cuda_fail(e, "launch_resolve");
+    return RTB_OK;
+}
+
+extern "C" int rtb_resolve(const float* accum, uint8_t* rgba, uint64_t n_pixels, float n_samples_override, int device) {
+    if (n_pixels && (!accum || !rgba)) return fail(RTB_ERR_INVALID_ARGUMENT, "accum/rgba is NULL");
+    if (n_pixels == 0) return RTB_OK;
+    int ndev = 0;
+    int rc = rtb_device_count(&ndev);
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaSetDevice(device));
+    float* d_acc = nullptr;
+    uint8_t* d_rgba = nullptr;
+    RTB_CUDA(cudaMalloc(&d_acc, n_pixels * 16));
+    cudaError_t e = cudaMalloc(&d_rgba, n_pixels * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_acc, accum, n_pixels * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = launch_resolve(reinterpret_cast<const float4*>(d_acc), reinterpret_cast<uchar4*>(d_rgba), n_pixels,
+                           n_samples_override, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(rgba, d_rgba, n_pixels * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_acc);
+    cudaFree(d_rgba);
+    if (e != cudaSuccess) return cuda_fail(e, "rtb_resolve");
+    return RTB_OK;
+}
+
+// Host-buffer render: upload accum, render, resolve, download.  `progress` (optional) is called
+// after every batch with the number of samples done; returning non-zero cancels.
+template <class Progress>
+static int render_host(RtbScene* scene, const RtbCamera* cam, const RtbRenderOptions* opt, float* accum,
+                       uint8_t* rgba, RtbRenderStats* stats, bool refresh_each_batch, Progress progress) {
+    int rc = check_render_args(scene, cam, opt);
+    if (rc != RTB_OK) return rc;
+    if (!accum) return fail(RTB_ERR_INVALID_ARGUMENT, "accum is NULL");
+    std::lock_guard<std::mutex> lock(scene->mutex);
+    RTB_CUDA(cudaSetDevice(scene->device));
+    const uint64_t npx = (uint64_t)cam->image_width * cam->image_height;
+    float* d_acc = nullptr;
+    uint8_t* d_rgba = nullptr;
+    RTB_CUDA(cudaMalloc(&d_acc, npx * 16));
+    cudaError_t e = rgba ? cudaMalloc(&d_rgba, npx * 4) : cudaSuccess;
+    if (e == cudaSuccess) e = cudaMemcpy(d_acc, accum, npx * 16, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d_acc);
+        cudaFree(d_rgba);
+        return cuda_fail(e, "rtb_render upload");
+    }
+    const uint32_t total = opt->sample_count ? opt->sample_count : cam->samples_per_pixel;
+    const uint32_t per_batch = opt->samples_per_launch ? opt->samples_per_launch : total;
+    RtbRenderStats acc_stats{};
+    bool cancelled = false;
+    for (uint32_t done = 0; done < total && rc == RTB_OK && !cancelled;) {
+        RtbRenderOptions o = *opt;
+        o.sample_begin = opt->sample_begin + done;
+        o.sample_count = (total - done < per_batch) ? total - done : per_batch;
+        o.samples_per_launch = o.sample_count;
+        if (o.sample_count == 0) break;
+        RtbRenderStats st{};
+        rc = render_device_locked(scene, cam, &o, d_acc, 0, &st);
+        if (rc != RTB_OK) break;
+        done += o.sample_count;
+        acc_stats.n_paths += st.n_paths;
+        acc_stats.n_rays += st.n_rays;
+        acc_stats.n_box_tests += st.n_box_tests;
+        acc_stats.n_object_tests += st.n_object_tests;
+        acc_stats.n_hits += st.n_hits;
+        acc_stats.device_ms += st.device_ms;
+        acc_stats.n_launches += st.n_launches;
+        const bool last = done >= total;
+        if (refresh_each_batch || last) {
+            if (d_rgba) {
+                e = launch_resolve(reinterpret_cast<const float4*>(d_acc), reinterpret_cast<uchar4*>(d_rgba), npx, 0.0f, 0);
+                acc_stats.n_launches += 1;
+                if (e == cudaSuccess) e = cudaMemcpy(rgba, d_rgba, npx * 4, cudaMemcpyDeviceToHost);
+            }
+            if (e == cudaSuccess) e = cudaMemcpy(accum, d_acc, npx * 16, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) {
+                rc = cuda_fail(e, "rtb_render download");
+                break;
+            }
+        }
+        if (progress(done) && !last) {
+            cancelled = true;
+            if (!refresh_each_batch) {  // hand back what has been rendered so far
+                if (d_rgba) {
+                    e = launch_resolve(reinterpret_cast<const float4*>(d_acc), reinterpret_cast<uchar4*>(d_rgba), npx, 0.0f, 0);
+                    if (e == cudaSuccess) e = cudaMemcpy(rgba, d_rgba, npx * 4, cudaMemcpyDeviceToHost);
+                }
+                if (e == cudaSuccess) e = cudaMemcpy(accum, d_acc, npx * 16, cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) rc = cuda_fail(e, "rtb_render download");
+            }
+        }
+    }
+    cudaFree(d_acc);
+    cudaFree(d_rgba);
+    if (stats) *stats = acc_stats;
+    if (rc == RTB_OK && cancelled) return fail(RTB_ERR_CANCELLED, "render cancelled");
+    return rc;
+}
+
+extern "C" int rtb_render(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions* options, float* accum,
+                          uint8_t* rgba, RtbRenderStats* stats) {
+    return render_host(scene, camera, options, accum, rgba, stats, false, [](uint32_t) { return 0; });
+}
+
+// ------------------------------------------------------------------ async jobs
+extern "C" int rtb_render_async(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions* options,
+                                float* accum, uint8_t* rgba, RtbJob** job_out) {
+    if (!job_out) return fail(RTB_ERR_INVALID_ARGUMENT, "job_out is NULL");
+    *job_out = nullptr;
+    int rc = check_render_args(scene, camera, options);
+    if (rc != RTB_OK) return rc;
+    if (!accum) return fail(RTB_ERR_INVALID_ARGUMENT, "accum is NULL");
+    RtbJob* job = new (std::nothrow) RtbJob();
+    if (!job) return fail(RTB_ERR_OUT_OF_MEMORY, "host allocation failed");
+    const RtbCamera cam = *camera;
+    RtbRenderOptions opt = *options;
+    job->samples_total = opt.sample_count ? opt.sample_count : cam.samples_per_pixel;
+    if (opt.samples_per_launch == 0) opt.samples_per_launch = 1;  // the reference refreshes after every sample
+    job->worker = std::thread([=]() {
+        RtbRenderStats st{};
+        const int r = render_host(scene, &cam, &opt, accum, rgba, &st, true, [job](uint32_t done) {
+            job->samples_done.store(done, std::memory_order_release);
+            return job->cancel.load(std::memory_order_acquire);
+        });
+        job->status = r;
+        if (r != RTB_OK) job->error = g_last_error;
+        job->stats = st;
+        job->running.store(0, std::memory_order_release);
+    });
+    *job_out = job;
+    return RTB_OK;
+}
+
+extern "C" int rtb_job_progress(RtbJob* job, uint32_t* samples_done, uint32_t* samples_total, int* running) {
+    if (!job) return fail(RTB_ERR_INVALID_ARGUMENT, "job is NULL");
+    if (samples_done) *samples_done = job->samples_done.load(std::memory_order_acquire);
+    if (samples_total) *samples_total = job->samples_total;
+    if (running) *running = job->running.load(std::memory_order_acquire);
+    return RTB_OK;
+}
+
+extern "C" int rtb_job_cancel(RtbJob* job) {
+    if (!job) return fail(RTB_ERR_INVALID_ARGUMENT, "job is NULL");
+    job->cancel.store(1, std::memory_order_release);
+    return RTB_OK;
+}
+
+extern "C" int rtb_job_wait(RtbJob* job, RtbRenderStats* stats) {
+    if (!job) return fail(RTB_ERR_INVALID_ARGUMENT, "job is NULL");
+    if (job->worker.joinable()) job->worker.join();
+    if (stats) *stats = job->stats;
+    if (job->status != RTB_OK) g_last_error = job->error;
+    return job->status;
+}
+
+extern "C" int rtb_job_destroy(RtbJob* job) {
+    if (!job) return RTB_OK;
+    job->cancel.store(1, std::memory_order_release);
+    if (job->worker.joinable()) job->worker.join();
+    delete job;
+    return RTB_OK;
+}
+
+// ------------------------------------------------------------------ RNG self-test
+extern "C" int rtb_philox_device_selftest(const uint32_t* counters4, const uint32_t* key2, uint32_t n, uint32_t* out4,
+                                          int device) {
+    if (n && (!counters4 || !key2 || !out4)) return fail(RTB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n == 0) return RTB_OK;
+    int ndev = 0;
+    int rc = rtb_device_count(&ndev);
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaSetDevice(device));
+    uint4 *d_in = nullptr, *d_out = nullptr;
+    RTB_CUDA(cudaMalloc(&d_in, (size_t)n * 16));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)n * 16);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, counters4, (size_t)n * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_philox_selftest(d_in, make_uint2(key2[0], key2[1]), n, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out4, d_out, (size_t)n * 16, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "rtb_philox_device_selftest");
+    return RTB_OK;
+}

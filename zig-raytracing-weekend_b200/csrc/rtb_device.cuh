@@ -1,0 +1,518 @@
+// rtb_device.cuh — device-side building blocks of the path-tracing hot path (sm_100a).
+//
+// Everything the reference does per ray segment, restated for one GPU thread:
+//   Camera.getRay          src/camera.zig:156-180      -> get_ray
+//   BVHNode.hit / Aabb.hit src/bvh.zig:122-136, src/aabb.zig:82-114 -> traverse_reference
+//   Sphere.hit             src/objects.zig:116-148     -> sphere_root / finish_sphere_hit
+//   Material.scatter       src/material.zig:18-106     -> shade
+//   Texture.value, Perlin  src/textures.zig:22-123, src/perlin.zig:30-152 -> texture_value
+//   RNG                    src/rtweekend.zig:14-16     -> Philox4x32-10 keyed (pixel,sample,segment,block)
+//
+// This translation unit is compiled with -fmad=false: Zig's float mode is strict, so no
+// multiply-add contraction may happen in decision arithmetic (slab test, discriminant, roots,
+// front_face) — the nearest-hit index must match the CPU semantics bit for bit.  Division and
+// square root are IEEE (nvcc defaults -prec-div=true -prec-sqrt=true, no --use_fast_math).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtb.h"
+
+namespace rtb {
+
+// ------------------------------------------------------------------ device scene layout
+// BVH re-laid out in DFS pre-order with skip links ("threaded" tree): visiting order is exactly
+// the reference's left-then-right recursion, with no stack.  One node = 2 x float4 (32 B):
+//   interior: f0 = {bmin.xyz, bits(KIND_INTERIOR<<30 | skip)}   f1 = {bmax.xyz, 0}
+//             hit  -> next = i + 1 (left child), miss -> next = skip (first node after the subtree)
+//   sphere  : f0 = {center1.xyz, bits(kind<<30 | object)}       f1 = {center_vec.xyz, radius}
+//             next = i + 1 (a leaf's successor in pre-order is the next node)
+//   quad    : f0 = {0,0,0, bits(KIND_QUAD<<30 | object)}        f1 = {0,0,0, bits(quad slot)}
+enum : uint32_t { KIND_INTERIOR = 0u, KIND_SPHERE = 1u, KIND_MOVING_SPHERE = 2u, KIND_QUAD = 3u };
+#define RTB_META_INDEX_MASK 0x3fffffffu
+
+// Material record, 2 x float4:
+//   m0 = {bits(type | tex_type << 8), bits(texture index), fuzz, ir}
+//   m1 = {albedo.rgb (metal) or inlined solid colour (lambertian/light/isotropic with a solid texture), 0}
+// Texture record, 3 x float4:
+//   t0 = {bits(type), bits(index), scale, 0}   t1 = {color.rgb, 0}   t2 = {color2.rgb, 0}
+struct DevImage {
+    const uchar4* texels;  // tightly packed RGBA8, row stride = width
+    uint32_t width, height;
+};
+struct DevPerlin {
+    float4 ranvec[256];
+    uint8_t perm_x[256], perm_y[256], perm_z[256];
+};
+struct DevQuad {  // Quad fields incl. the ones Quad.init derives (src/objects.zig:195-211)
+    float4 q_d;       // q.xyz, d
+    float4 u;         // u.xyz
+    float4 v;         // v.xyz
+    float4 normal;    // normal.xyz
+    float4 w;         // w.xyz
+};
+
+struct DevScene {
+    const float4* nodes;  // 2 per node
+    uint32_t n_nodes;
+    uint32_t n_objects;
+    const uint32_t* object_material;  // object index -> material index
+    const float4* materials;          // 2 per material
+    const float4* textures;           // 3 per texture
+    const DevPerlin* perlins;
+    const DevImage* images;
+    const DevQuad* quads;
+    uint32_t has_quads;
+};
+
+struct DevCamera {
+    float3 center, pixel00, du, dv, ddu, ddv, background;
+    float defocus_angle;
+    uint32_t width, height, max_depth, background_mode;
+};
+
+// ------------------------------------------------------------------ vec3.zig (element-wise, unfused)
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 f3(float4 v) { return make_float3(v.x, v.y, v.z); }
+__device__ __forceinline__ float3 splat3(float s) { return make_float3(s, s, s); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float length_squared(float3 u) { return u.x * u.x + u.y * u.y + u.z * u.z; }
+__device__ __forceinline__ float dot3(float3 u, float3 v) { return u.x * v.x + u.y * v.y + u.z * v.z; }
+__device__ __forceinline__ float3 cross3(float3 u, float3 v) {
+    return f3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+}
+__device__ __forceinline__ float3 unit_vector(float3 v) { return v / splat3(sqrtf(length_squared(v))); }
+__device__ __forceinline__ float3 reflect3(float3 v, float3 n) { return v - n * splat3(dot3(v, n) * 2.0f); }
+__device__ __forceinline__ float3 refract3(float3 uv, float3 n, float etai_over_etat) {
+    const float cos_theta = fminf(dot3(-uv, n), 1.0f);
+    const float3 r_out_perp = splat3(etai_over_etat) * (uv + n * splat3(cos_theta));
+    const float3 r_out_parallel = n * splat3(-sqrtf(fabsf(1.0f - length_squared(r_out_perp))));
+    return r_out_perp + r_out_parallel;
+}
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+struct RngKey {
+    uint2 seed;
+    uint32_t pixel, sample;
+};
+__device__ __forceinline__ float4 rng_block(const RngKey& k, uint32_t segment, uint32_t block) {
+    const uint4 o = philox4x32_10(make_uint4(k.pixel, k.sample, segment, block), k.seed);
+    return make_float4(u01(o.x), u01(o.y), u01(o.z), u01(o.w));
+}
+// randomDoubleRange(-1, 1) = min + (max - min) * r   (src/rtweekend.zig:18-20)
+__device__ __forceinline__ float range_pm1(float r) { return -1.0f + 2.0f * r; }
+
+// vec3.randomUnitVector (src/vec3.zig:59-68); try j = words 0..2 of block j of this segment.
+__device__ __forceinline__ float3 random_unit_vector(const RngKey& k, uint32_t segment, float4 block0) {
+    float4 b = block0;
+    for (uint32_t j = 0;; ++j) {
+        if (j) b = rng_block(k, segment, j);
+        const float3 p = f3(range_pm1(b.x), range_pm1(b.y), range_pm1(b.z));
+        if (length_squared(p) < 1.0f) return unit_vector(p);
+    }
+}
+
+// ------------------------------------------------------------------ rays
+struct DRay {
+    float3 o, d;
+    float time;
+};
+
+// Camera.getRay (src/camera.zig:169-180) for flat pixel index (x = i % W + 1, y = i / W + 1,
+// 1-based: src/camera.zig:100-101).  Stream segment 0: block 0 = (jitter x, jitter y, time, -),
+// defocus-disk try j = block 1 + (j >> 1), words 2(j&1), 2(j&1)+1.
+__device__ __forceinline__ DRay get_ray(const DevCamera& cam, const RngKey& k) {
+    const uint32_t x = k.pixel % cam.width + 1u;
+    const uint32_t y = k.pixel / cam.width + 1u;
+    const float4 b0 = rng_block(k, 0u, 0u);
+    const float3 pixel_center = cam.pixel00 + cam.du * splat3((float)x) + cam.dv * splat3((float)y);
+    const float px = -0.5f + b0.x;
+    const float py = -0.5f + b0.y;
+    const float3 pixel_sample = pixel_center + (splat3(px) * cam.du + splat3(py) * cam.dv);
+    float3 origin = cam.center;
+    if (!(cam.defocus_angle <= 0.0f)) {
+        float px_d, py_d;
+        for (uint32_t j = 0;; ++j) {
+            const float4 b = rng_block(k, 0u, 1u + (j >> 1));
+            px_d = range_pm1((j & 1u) ? b.z : b.x);
+            py_d = range_pm1((j & 1u) ? b.w : b.y);
+            if (px_d * px_d + py_d * py_d + 0.0f * 0.0f < 1.0f) break;
+        }
+        origin = cam.center + cam.ddu * splat3(px_d) + cam.ddv * splat3(py_d);
+    }
+    DRay r;
+    r.o = origin;
+    r.d = pixel_sample - origin;
+    r.time = b0.z;
+    return r;
+}
+
+// ------------------------------------------------------------------ traversal
+struct Nearest {
+    float t;        // closest accepted root so far (doubles as ray_t.max)
+    uint32_t node;  // pre-order index of the leaf that produced it, 0xffffffff = none
+};
+
+// Sphere.hit up to the accepted root (src/objects.zig:121-137).  `center` already includes the
+// motion term.  Returns true and the root iff it lies strictly inside (t_min, t_max).
+__device__ __forceinline__ bool sphere_root(const DRay& r, float3 center, float radius, float t_min, float t_max,
+                                            float& root_out) {
+    const float3 oc = r.o - center;
+    const float a = length_squared(r.d);
+    const float half_b = dot3(oc, r.d);
+    const float c = length_squared(oc) - radius * radius;
+    const float discriminant = half_b * half_b - a * c;
+    if (discriminant < 0.0f) return false;
+    const float sqrtd = sqrtf(discriminant);
+    float root = (-half_b - sqrtd) / a;
+    if (!(t_min < root && root < t_max)) {  // Interval.surrounds, src/interval.zig:12-14
+        root = (-half_b + sqrtd) / a;
+        if (!(t_min < root && root < t_max)) return false;
+    }
+    root_out = root;
+    return true;
+}
+
+// Quad.hit (src/objects.zig:226-261); returns t and the planar coordinates.
+__device__ __forceinline__ bool quad_root(const DRay& r, const DevQuad& qd, float t_min, float t_max, float& t_out,
+                                          float& alpha_out, float& beta_out) {
+    const float3 normal = f3(qd.normal);
+    const float denom = dot3(normal, r.d);
+    if (fabsf(denom) < 1e-8f) return false;
+    const float t = (qd.q_d.w - dot3(normal, r.o)) / denom;
+    if (!(t_min <= t && t <= t_max)) return false;  // Interval.contains, src/interval.zig:8-10
+    const float3 intersection = r.o + splat3(t) * r.d;
+    const float3 planar = intersection - f3(qd.q_d);
+    const float alpha = dot3(f3(qd.w), cross3(planar, f3(qd.v)));
+    const float beta = dot3(f3(qd.w), cross3(f3(qd.u), planar));
+    if ((alpha < 0.0f) || (1.0f < alpha) || (beta < 0.0f) || (1.0f < beta)) return false;
+    t_out = t;
+    alpha_out = alpha;
+    beta_out = beta;
+    return true;
+}
+
+// BVHTree.hit in the reference's visiting order (src/bvh.zig:122-136) over the threaded layout.
+//   * interior node: Aabb.hit with ray_t = (t_min, closest so far)  (src/aabb.zig:82-114);
+//     1/direction is hoisted out of the loop (the reference recomputes the same IEEE quotient at
+//     every node); the per-axis early-outs are folded into one final test, which is equivalent
+//     because t_min only grows and t_max only shrinks and NaNs never enter them.
+//   * leaf: primitive test directly, no box test.
+//   * a later hit replaces an earlier one only if strictly nearer (Interval.surrounds is strict),
+//     so ties go to the DFS-earlier object, as in `hit_record_right orelse hit_record_left`.
+template <bool COUNT, bool QUADS>
+__device__ __forceinline__ Nearest traverse_reference(const float4* __restrict__ nodes, uint32_t n_nodes,
+                                                      const DevQuad* __restrict__ quads, const DRay& r, float t_min,
+                                                      float t_max, uint32_t& n_box, uint32_t& n_obj) {
+    Nearest best;
+    best.t = t_max;
+    best.node = 0xffffffffu;
+    const float inv_x = 1.0f / r.d.x, inv_y = 1.0f / r.d.y, inv_z = 1.0f / r.d.z;
+    uint32_t i = 0;
+    while (i < n_nodes) {
+        const float4 f0 = nodes[2u * i];
+        const float4 f1 = nodes[2u * i + 1u];
+        const uint32_t meta = __float_as_uint(f0.w);
+        const uint32_t kind = meta >> 30;
+        if (kind == KIND_INTERIOR) {
+            if (COUNT) ++n_box;
+            float t0x = (f0.x - r.o.x) * inv_x, t1x = (f1.x - r.o.x) * inv_x;
+            float t0y = (f0.y - r.o.y) * inv_y, t1y = (f1.y - r.o.y) * inv_y;
+            float t0z = (f0.z - r.o.z) * inv_z, t1z = (f1.z - r.o.z) * inv_z;
+            if (inv_x < 0.0f) { const float s = t0x; t0x = t1x; t1x = s; }
+            if (inv_y < 0.0f) { const float s = t0y; t0y = t1y; t1y = s; }
+            if (inv_z < 0.0f) { const float s = t0z; t0z = t1z; t1z = s; }
+            float lo = t_min, hi = best.t;
+            if (t0x > lo) lo = t0x;
+            if (t1x < hi) hi = t1x;
+            if (t0y > lo) lo = t0y;
+            if (t1y < hi) hi = t1y;
+            if (t0z > lo) lo = t0z;
+            if (t1z < hi) hi = t1z;
+            i = (hi <= lo) ? (meta & RTB_META_INDEX_MASK) : i + 1u;
+        } else {
+            if (COUNT) ++n_obj;
+            if (!QUADS || kind != KIND_QUAD) {
+                const float3 c1 = f3(f0);
+                const float3 center = (kind == KIND_MOVING_SPHERE) ? c1 + splat3(r.time) * f3(f1) : c1;
+                float root;
+                if (sphere_root(r, center, f1.w, t_min, best.t, root)) {
+                    best.t = root;
+                    best.node = i;
+                }
+            } else {
+                float t, alpha, beta;
+                if (quad_root(r, quads[__float_as_uint(f1.w)], t_min, best.t, t, alpha, beta)) {
+                    best.t = t;
+                    best.node = i;
+                }
+            }
+            i = i + 1u;
+        }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------ hit record (src/objects.zig:21-37)
+struct DHit {
+    float3 p, normal;
+    float t, u, v;
+    uint32_t object;
+    bool front_face;
+};
+
+// getSphereUV (src/objects.zig:101-114)
+__device__ __forceinline__ void sphere_uv(float3 p, float& u, float& v) {
+    const float pi = 3.1415926535897932385f;
+    const float theta = acosf(-p.y);
+    const float phi = atan2f(-p.z, p.x) + pi;
+    u = phi / (2.0f * pi);
+    v = theta / pi;
+}
+
+// The part of Sphere.hit / Quad.hit after the root is accepted (src/objects.zig:139-147, :250-260),
+// evaluated once for the nearest hit instead of once per candidate.
+template <bool QUADS, bool WANT_UV>
+__device__ __forceinline__ DHit finish_hit(const float4* __restrict__ nodes, const DevQuad* __restrict__ quads,
+                                           const DRay& r, Nearest best) {
+    DHit h;
+    const float4 f0 = nodes[2u * best.node];
+    const float4 f1 = nodes[2u * best.node + 1u];
+    const uint32_t meta = __float_as_uint(f0.w);
+    const uint32_t kind = meta >> 30;
+    h.object = meta & RTB_META_INDEX_MASK;
+    h.t = best.t;
+    h.p = r.o + splat3(best.t) * r.d;  // Ray.at, src/ray.zig:9-11
+    h.u = 0.0f;
+    h.v = 0.0f;
+    float3 outward;
+    if (!QUADS || kind != KIND_QUAD) {
+        const float3 c1 = f3(f0);
+        const float3 center = (kind == KIND_MOVING_SPHERE) ? c1 + splat3(r.time) * f3(f1) : c1;
+        outward = (h.p - center) / splat3(f1.w);
+        if (WANT_UV) sphere_uv(outward, h.u, h.v);
+    } else {
+        const DevQuad& qd = quads[__float_as_uint(f1.w)];
+        outward = f3(qd.normal);
+        if (WANT_UV) {  // isInterior, src/objects.zig:217-224
+            const float3 planar = h.p - f3(qd.q_d);
+            h.u = dot3(f3(qd.w), cross3(planar, f3(qd.v)));
+            h.v = dot3(f3(qd.w), cross3(f3(qd.u), planar));
+        }
+    }
+    h.front_face = dot3(r.d, outward) < 0.0f;  // setFaceNormal, src/objects.zig:30-36
+    h.normal = h.front_face ? outward : -outward;
+    return h;
+}
+
+// ------------------------------------------------------------------ textures
+// perlin_interp + Perlin.noise (src/perlin.zig:30-53, :117-152).  (i_f*uu + (1-i_f)*(1-uu)) is
+// exactly uu for i=1 and (1-uu) for i=0, so the weights are selected instead of computed.
+__device__ __forceinline__ float perlin_noise(const DevPerlin& pl, float3 p) {
+    const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    const float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    const int i = (int)fx, j = (int)fy, k = (int)fz;
+    const float uu = u * u * (3.0f - 2.0f * u);
+    const float vv = v * v * (3.0f - 2.0f * v);
+    const float ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                const uint32_t idx =
+                    pl.perm_x[(i + di) & 255] ^ pl.perm_y[(j + dj) & 255] ^ pl.perm_z[(k + dk) & 255];
+                const float4 g = pl.ranvec[idx];
+                const float3 weight_v = f3(u - (float)di, v - (float)dj, w - (float)dk);
+                const float wu = di ? uu : (1.0f - uu);
+                const float wv = dj ? vv : (1.0f - vv);
+                const float ww_ = dk ? ww : (1.0f - ww);
+                accum += wu * wv * ww_ * dot3(f3(g), weight_v);
+            }
+    return accum;
+}
+// Perlin.turb (src/perlin.zig:103-115)
+__device__ __forceinline__ float perlin_turb(const DevPerlin& pl, float3 p, int depth) {
+    float accum = 0.0f;
+    float3 temp_p = p;
+    float weight = 1.0f;
+    for (int i = 0; i < depth; ++i) {
+        accum += weight * perlin_noise(pl, temp_p);
+        weight *= 0.5f;
+        temp_p = temp_p * splat3(2.0f);
+    }
+    return fabsf(accum);
+}
+
+__device__ __forceinline__ bool texture_needs_uv(uint32_t tex_type) { return tex_type == RTB_TEX_IMAGE; }
+
+// Texture.value (src/textures.zig:22-26) for the non-solid variants.
+struct TexTables {
+    const float4* textures;
+    const DevPerlin* perlins;
+    const DevImage* images;
+};
+static __device__ __noinline__ float3 texture_value_slow(TexTables sc, uint32_t tex, float u, float v, float3 p) {
+    const float4 t0 = sc.textures[3u * tex];
+    const uint32_t type = __float_as_uint(t0.x);
+    const uint32_t index = __float_as_uint(t0.y);
+    if (type == RTB_TEX_CHECKER) {  // src/textures.zig:60-72
+        const int xi = (int)floorf(t0.z * p.x);
+        const int yi = (int)floorf(t0.z * p.y);
+        const int zi = (int)floorf(t0.z * p.z);
+        const bool is_even = ((xi + yi + zi) % 2) == 0;
+        return f3(sc.textures[3u * tex + (is_even ? 1u : 2u)]);
+    }
+    if (type == RTB_TEX_IMAGE) {  // src/textures.zig:85-104, src/rtw_image.zig:37-62
+        const DevImage im = sc.images[index];
+        if (im.height == 0u) return f3(0.0f, 1.0f, 1.0f);
+        const float new_u = u < 0.0f ? 0.0f : (u > 1.0f ? 1.0f : u);
+        const float cv = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+        const float new_v = 1.0f - cv;
+        uint32_t i = (uint32_t)floorf(new_u * (float)im.width);
+        uint32_t j = (uint32_t)floorf(new_v * (float)im.height);
+        if (!(i < im.width)) i = im.width - 1u;
+        if (!(j < im.height)) j = im.height - 1u;
+        const uchar4 px = im.texels[(size_t)j * im.width + i];
+        const float color_scale = 1.0f / 255.0f;
+        return f3(color_scale * (float)px.x, color_scale * (float)px.y, color_scale * (float)px.z);
+    }
+    if (type == RTB_TEX_NOISE) {  // src/textures.zig:118-123
+        const float3 s = splat3(t0.z) * p;
+        return splat3(0.5f * (1.0f + sinf(s.z + 10.0f * perlin_turb(sc.perlins[index], s, 7))));
+    }
+    return f3(sc.textures[3u * tex + 1u]);  // solid
+}
+
+// ------------------------------------------------------------------ materials
+// reflectance (src/material.zig:101-106); (1-cos)^5 by repeated multiplication.
+__device__ __forceinline__ float schlick(float cosine, float ref_idx) {
+    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    r0 = r0 * r0;
+    const float x = 1.0f - cosine;
+    const float x2 = x * x;
+    return r0 + (1.0f - r0) * (x2 * x2 * x);
+}
+
+struct ShadeResult {
+    float3 emitted;
+    float3 attenuation;
+    DRay scattered;
+    bool scatters;
+};
+
+// emitted + scatter for the nearest hit (src/camera.zig:194-196 -> src/material.zig:18-30).
+// `segment` (>= 1) keys this hit's RNG stream; block 0 word 3 is the dielectric reflectance draw.
+template <bool QUADS>
+__device__ __forceinline__ ShadeResult shade(const DevScene& sc, const float4* __restrict__ nodes, const DRay& r,
+                                             Nearest best, const RngKey& key, uint32_t segment) {
+    ShadeResult out;
+    const TexTables tt{sc.textures, sc.perlins, sc.images};
+    out.emitted = f3(0.0f, 0.0f, 0.0f);
+    const uint32_t object = __float_as_uint(nodes[2u * best.node].w) & RTB_META_INDEX_MASK;
+    const uint32_t mat = sc.object_material[object];
+    const float4 m0 = sc.materials[2u * mat];
+    const float4 m1 = sc.materials[2u * mat + 1u];
+    const uint32_t tag = __float_as_uint(m0.x);
+    const uint32_t type = tag & 0xffu;
+    const uint32_t tex_type = (tag >> 8) & 0xffu;
+    DHit h;
+    if (texture_needs_uv(tex_type))
+        h = finish_hit<QUADS, true>(nodes, sc.quads, r, best);
+    else
+        h = finish_hit<QUADS, false>(nodes, sc.quads, r, best);
+    out.scattered.o = h.p;
+    out.scattered.time = r.time;
+    if (type == RTB_MAT_LAMBERTIAN) {  // src/material.zig:43-54
+        const float4 b0 = rng_block(key, segment, 0u);
+        float3 dir = h.normal + random_unit_vector(key, segment, b0);
+        const float s = 1e-8f;
+        if (fabsf(dir.x) < s && fabsf(dir.y) < s && fabsf(dir.z) < s) dir = h.normal;  // nearZero
+        out.scattered.d = dir;
+        out.attenuation =
+            (tex_type == RTB_TEX_SOLID) ? f3(m1) : texture_value_slow(tt, __float_as_uint(m0.y), h.u, h.v, h.p);
+        out.scatters = true;
+    } else if (type == RTB_MAT_METAL) {  // src/material.zig:65-70
+        const float4 b0 = rng_block(key, segment, 0u);
+        const float3 reflected = reflect3(unit_vector(r.d), h.normal);
+        out.scattered.d = reflected + splat3(m0.z) * random_unit_vector(key, segment, b0);
+        out.attenuation = f3(m1);
+        out.scatters = dot3(out.scattered.d, h.normal) > 0.0f;
+    } else if (type == RTB_MAT_DIELECTRIC) {  // src/material.zig:80-98
+        out.attenuation = f3(1.0f, 1.0f, 1.0f);
+        const float refraction_ratio = h.front_face ? (1.0f / m0.w) : m0.w;
+        const float3 unit_direction = unit_vector(r.d);
+        const float cos_theta = fminf(dot3(-unit_direction, h.normal), 1.0f);
+        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        const bool cannot_refract = refraction_ratio * sin_theta > 1.0f;
+        bool do_reflect = cannot_refract;
+        if (!do_reflect) do_reflect = schlick(cos_theta, refraction_ratio) > rng_block(key, segment, 0u).w;
+        out.scattered.d =
+            do_reflect ? reflect3(unit_direction, h.normal) : refract3(unit_direction, h.normal, refraction_ratio);
+        out.scatters = true;
+    } else if (type == RTB_MAT_DIFFUSE_LIGHT) {  // src/material.zig:119-125
+        out.emitted =
+            (tex_type == RTB_TEX_SOLID) ? f3(m1) : texture_value_slow(tt, __float_as_uint(m0.y), h.u, h.v, h.p);
+        out.attenuation = f3(0.0f, 0.0f, 0.0f);
+        out.scattered.d = f3(0.0f, 0.0f, 0.0f);
+        out.scatters = false;
+    } else {  // isotropic, src/material.zig:139-143
+        const float4 b0 = rng_block(key, segment, 0u);
+        out.scattered.d = random_unit_vector(key, segment, b0);
+        out.attenuation =
+            (tex_type == RTB_TEX_SOLID) ? f3(m1) : texture_value_slow(tt, __float_as_uint(m0.y), h.u, h.v, h.p);
+        out.scatters = true;
+    }
+    return out;
+}
+
+// Miss colour: solid background (src/camera.zig:207) or the legacy sky gradient (:204-206).
+__device__ __forceinline__ float3 miss_color(const DevCamera& cam, const DRay& r) {
+    if (cam.background_mode == RTB_BACKGROUND_SKY) {
+        const float3 unit_direction = unit_vector(r.d);
+        const float a = 0.5f * (unit_direction.y + 1.0f);
+        return f3(1.0f, 1.0f, 1.0f) * splat3(1.0f - a) + f3(0.5f, 0.7f, 1.0f) * splat3(a);
+    }
+    return cam.background;
+}
+
+// color.toGamma2 + @intFromFloat (src/color.zig:43-62, src/camera.zig:57-65); NaN -> 0
+// (the reference's @intFromFloat(NaN) is undefined behaviour).
+__device__ __forceinline__ uchar4 quantise(float4 acc, float n) {
+    const float scale = 1.0f / n;
+    float c[3] = {acc.x, acc.y, acc.z};
+    uint8_t o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float x = c[k] * scale;
+        x = sqrtf(x);
+        if (x < 0.0f) x = 0.0f;
+        if (x > 0.999f) x = 0.999f;
+        float g = 256.0f * x;
+        if (!(g == g)) g = 0.0f;
+        o[k] = (uint8_t)g;
+    }
+    return make_uchar4(o[0], o[1], o[2], 255);
+}
+
+}  // namespace rtb

@@ -1,0 +1,219 @@
+// rtb_kernels.cu — CUDA kernels of the path-tracing hot path, sm_100a, compiled -fmad=false.
+//
+//   K1 render_megakernel : Camera.render + getRay + rayColor per pixel (src/camera.zig:93-208)
+//   K3 trace_kernel      : world.hit for explicit ray batches           (src/bvh.zig:39-41)
+//   K4 resolve_kernel    : toGamma2 + RGBA8 quantise                    (src/color.zig:43-62)
+#include "rtb_kernels.cuh"
+
+namespace rtb {
+
+// ------------------------------------------------------------------------------------------
+// K1 — megakernel.
+//
+// One thread owns one pixel for all the samples of this launch and keeps the running sum in
+// registers, adding samples in sample order onto the value already in the accumulation buffer —
+// exactly the order in which SharedStateImageWriter.writeColor adds them (src/camera.zig:54-56).
+// Paths are regenerated in place: the loop body is "one ray segment"; when a lane's path ends it
+// starts its next sample at once, so the warp stays converged on the traversal loop instead of
+// idling until its longest path finishes.
+// ------------------------------------------------------------------------------------------
+template <bool SMEM_NODES, bool COUNT, bool QUADS>
+__global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderParams P) {
+    extern __shared__ float4 s_nodes[];
+    const float4* __restrict__ nodes = P.scene.nodes;
+    if (SMEM_NODES) {
+        for (uint32_t i = threadIdx.x; i < 2u * P.scene.n_nodes; i += kCtaThreads) s_nodes[i] = P.scene.nodes[i];
+        __syncthreads();
+        nodes = s_nodes;
+    }
+
+    const uint32_t tiles_x = (P.cam.width + kTileW - 1u) / kTileW;
+    const uint32_t tile = blockIdx.x * P.tile_world + P.tile_rank;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t px = (tile % tiles_x) * kTileW + (warp & 3u) * 8u + (lane & 7u);
+    const uint32_t py = (tile / tiles_x) * kTileH + (warp >> 2) * 4u + (lane >> 3);
+    const uint32_t pixel = py * P.cam.width + px;
+    const bool active = px < P.cam.width && py < P.cam.height && pixel >= P.pixel_begin && pixel < P.pixel_end;
+
+    uint32_t n_rays = 0, n_box = 0, n_obj = 0, n_hits = 0;
+    if (active && P.sample_count > 0u) {
+        float4 acc = P.accum[pixel];
+        const uint32_t s_end = P.sample_begin + P.sample_count;
+        RngKey key;
+        key.seed = P.seed;
+        key.pixel = pixel;
+        key.sample = P.sample_begin;
+        if (P.cam.max_depth > 0u) {
+            DRay ray = get_ray(P.cam, key);
+            float3 T = f3(1.0f, 1.0f, 1.0f);
+            float3 L = f3(0.0f, 0.0f, 0.0f);
+            uint32_t segment = 1u;
+            for (;;) {
+                if (COUNT) ++n_rays;
+                const Nearest best = traverse_reference<COUNT, QUADS>(nodes, P.scene.n_nodes, P.scene.quads, ray,
+                                                                      0.001f, __int_as_float(0x7f800000), n_box, n_obj);
+                bool done;
+                if (best.node == 0xffffffffu) {
+                    L = L + T * miss_color(P.cam, ray);
+                    done = true;
+                } else {
+                    if (COUNT) ++n_hits;
+                    const ShadeResult sr = shade<QUADS>(P.scene, nodes, ray, best, key, segment);
+                    L = L + T * sr.emitted;
+                    if (sr.scatters && segment < P.cam.max_depth) {
+                        T = T * sr.attenuation;
+                        ray = sr.scattered;
+                        ++segment;
+                        done = false;
+                    } else {
+                        done = true;
+                    }
+                }
+                if (done) {
+                    acc.x += L.x;
+                    acc.y += L.y;
+                    acc.z += L.z;
+                    if (++key.sample == s_end) break;
+                    ray = get_ray(P.cam, key);
+                    T = f3(1.0f, 1.0f, 1.0f);
+                    L = f3(0.0f, 0.0f, 0.0f);
+                    segment = 1u;
+                }
+            }
+        }
+        acc.w = (float)s_end;  // buffer[i][3] = number_of_samples (src/camera.zig:56)
+        P.accum[pixel] = acc;
+    }
+    if (COUNT) {
+        unsigned long long v[4] = {n_rays, n_box, n_obj, n_hits};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned long long x = v[k];
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+            if (lane == 0 && x) atomicAdd(&P.counters[k], x);
+        }
+    }
+}
+
+template <bool SMEM, bool COUNT, bool QUADS>
+static cudaError_t launch_mega_variant(const RenderParams& p, uint32_t grid, size_t smem, cudaStream_t stream) {
+    auto kernel = render_megakernel<SMEM, COUNT, QUADS>;
+    if (smem > 48u * 1024u) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kernel<<<grid, kCtaThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+size_t megakernel_max_smem_nodes_bytes() { return 96u * 1024u; }
+
+cudaError_t launch_megakernel(const RenderParams& p, bool nodes_in_smem, bool count_work, cudaStream_t stream,
+                              LaunchInfo* info) {
+    const uint32_t tiles_x = (p.cam.width + kTileW - 1u) / kTileW;
+    const uint32_t tiles_y = (p.cam.height + kTileH - 1u) / kTileH;
+    const uint32_t tiles = tiles_x * tiles_y;
+    const uint32_t world = p.tile_world ? p.tile_world : 1u;
+    if (p.tile_rank >= world) return cudaErrorInvalidValue;
+    const uint32_t grid = (tiles > p.tile_rank) ? (tiles - p.tile_rank + world - 1u) / world : 0u;
+    if (grid == 0u) return cudaSuccess;
+    RenderParams q = p;
+    q.tile_world = world;
+    const size_t smem = nodes_in_smem ? (size_t)p.scene.n_nodes * 32u : 0u;
+    const bool quads = p.scene.has_quads != 0u;
+    cudaError_t e;
+#define RTB_DISPATCH(S, C, Q) e = launch_mega_variant<S, C, Q>(q, grid, smem, stream)
+    if (nodes_in_smem) {
+        if (count_work) { if (quads) RTB_DISPATCH(true, true, true); else RTB_DISPATCH(true, true, false); }
+        else            { if (quads) RTB_DISPATCH(true, false, true); else RTB_DISPATCH(true, false, false); }
+    } else {
+        if (count_work) { if (quads) RTB_DISPATCH(false, true, true); else RTB_DISPATCH(false, true, false); }
+        else            { if (quads) RTB_DISPATCH(false, false, true); else RTB_DISPATCH(false, false, false); }
+    }
+#undef RTB_DISPATCH
+    if (e == cudaSuccess && info) info->n_launches += 1;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 — ray queries.  One thread per ray, reference visiting order, full HitRecord.
+// ------------------------------------------------------------------------------------------
+template <bool QUADS>
+__global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const RtbRay* __restrict__ rays, uint64_t n,
+                                                    RtbHit* __restrict__ hits) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RtbRay rr = rays[i];
+    DRay r;
+    r.o = f3(rr.origin[0], rr.origin[1], rr.origin[2]);
+    r.d = f3(rr.direction[0], rr.direction[1], rr.direction[2]);
+    r.time = rr.time;
+    uint32_t n_box = 0, n_obj = 0;
+    const Nearest best =
+        traverse_reference<true, QUADS>(scene.nodes, scene.n_nodes, scene.quads, r, rr.t_min, rr.t_max, n_box, n_obj);
+    RtbHit h;
+    h.object = -1;
+    h.front_face = 0u;
+    h.t = 0.0f;
+    h.p[0] = h.p[1] = h.p[2] = 0.0f;
+    h.normal[0] = h.normal[1] = h.normal[2] = 0.0f;
+    h.u = h.v = 0.0f;
+    if (best.node != 0xffffffffu) {
+        const DHit d = finish_hit<QUADS, true>(scene.nodes, scene.quads, r, best);
+        h.object = (int32_t)d.object;
+        h.front_face = d.front_face ? 1u : 0u;
+        h.t = d.t;
+        h.p[0] = d.p.x; h.p[1] = d.p.y; h.p[2] = d.p.z;
+        h.normal[0] = d.normal.x; h.normal[1] = d.normal.y; h.normal[2] = d.normal.z;
+        h.u = d.u;
+        h.v = d.v;
+    }
+    h.n_box_tests = n_box;
+    h.n_object_tests = n_obj;
+    hits[i] = h;
+}
+
+cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n, RtbHit* d_hits,
+                         cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t grid = (uint32_t)((n + 255u) / 256u);
+    if (scene.has_quads)
+        trace_kernel<true><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
+    else
+        trace_kernel<false><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 — resolve.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resolve_kernel(const float4* __restrict__ accum, uchar4* __restrict__ rgba,
+                                                      uint64_t n_pixels, float n_override) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += stride) {
+        const float4 a = accum[i];
+        rgba[i] = quantise(a, n_override > 0.0f ? n_override : a.w);
+    }
+}
+
+cudaError_t launch_resolve(const float4* d_accum, uchar4* d_rgba, uint64_t n_pixels, float n_override,
+                           cudaStream_t stream) {
+    if (n_pixels == 0) return cudaSuccess;
+    uint64_t blocks = (n_pixels + 255u) / 256u;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    resolve_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(d_accum, d_rgba, n_pixels, n_override);
+    return cudaGetLastError();
+}
+
+__global__ void philox_selftest_kernel(const uint4* __restrict__ ctr, uint2 key, uint32_t n, uint4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = philox4x32_10(ctr[i], key);
+}
+
+cudaError_t launch_philox_selftest(const uint4* d_ctr, uint2 key, uint32_t n, uint4* d_out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    philox_selftest_kernel<<<(n + 127u) / 128u, 128, 0, stream>>>(d_ctr, key, n, d_out);
+    return cudaGetLastError();
+}
+
+}  // namespace rtb
