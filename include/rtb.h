@@ -194,10 +194,12 @@ enum {
     /* Reference order: left subtree, then right with t_max shrunk to the left hit; leaves are not
      * box-tested (src/bvh.zig:122-136).  Bit-exact nearest-hit index against the oracle. */
     RTB_TRAVERSAL_REFERENCE = 0,
-    /* Same tree, same intersection arithmetic, but leaves are box-tested before the primitive
-     * (conservative cull; differs from the reference only where fp rounding puts a sphere root
-     * outside its own float box). */
-    RTB_TRAVERSAL_CULL_LEAVES = 1
+    /* Same tree, same slab / sphere arithmetic, but at every interior node the child the ray meets
+     * first (by the sign of its direction on the axis separating the children) is visited first, so
+     * hits are found earlier and more subtrees are culled.  The nearest hit can differ from the
+     * reference's only where float rounding puts a sphere's root on the other side of its own box
+     * (measured: tests/test_gpu_parity.py::test_ordered_traversal_agrees). */
+    RTB_TRAVERSAL_ORDERED = 1
 };
 
 enum {
@@ -212,7 +214,7 @@ typedef struct RtbRenderOptions {
      * pixel_begin = thread_idx*chunk_size, pixel_count = chunk_size.  0/0 means the whole frame. */
     uint32_t pixel_begin;
     uint32_t pixel_count;
-    /* Interleaved-tile partition for multi-GPU: of the 32-pixel-wide x 4-row tiles inside the pixel
+    /* Interleaved-tile partition for multi-GPU: of the 32-pixel-wide x 8-row tiles inside the pixel
      * range, this call renders those with tile_index % tile_world == tile_rank.  0/0 or 0/1 = all. */
     uint32_t tile_rank;
     uint32_t tile_world;
@@ -318,6 +320,12 @@ int rtb_job_destroy(RtbJob* job);
  * device for n counters; replaces std.crypto.random.float (src/rtweekend.zig:14-16). */
 int rtb_philox_device_selftest(const uint32_t* counters4, const uint32_t* key2, uint32_t n,
                                uint32_t* out4, int device);
+
+/* Measurement aid for the roofline: runs a dependent-chain FFMA microbenchmark (8 independent chains
+ * per thread, full grid) on `device` and returns the best-of-5 rate in TFLOP/s counting one FMA as two
+ * flops.  The path tracer itself is compiled without multiply-add contraction, so its own ceiling is
+ * half of this figure. */
+int rtb_measure_fp32_peak(int device, double* tflops_out);
 
 #ifdef __cplusplus
 }

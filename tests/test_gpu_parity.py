@@ -367,3 +367,48 @@ def test_full_size_properties_config2(pkg, book1):
     c, _, _ = scene.render(cam, pkg.render_options(seed=1234, sample_begin=5, sample_count=3), accum=c)
     assert np.array_equal(a, c)
     assert 2.0 < st["n_rays"] / st["n_paths"] < 6.0
+
+
+def test_ordered_traversal_agrees(pkg, orc, book1):
+    """RTB_TRAVERSAL_ORDERED (near-child-first per octant): same tree, same slab/sphere arithmetic, different
+    visiting order.  The nearest hit may differ from the reference's only where float rounding puts a sphere root
+    outside its own box; measure it on incoherent rays and require (near-)total agreement."""
+    world, scene = book1
+    cam = pkg.book1_camera(400, 10, 50).init()
+    rng = np.random.default_rng(11)
+    rays = np.concatenate([_rays_from_camera(orc, cam, 5, 30000, rng), _random_rays(pkg, rng, 30000, -12, 12)])
+    ref = scene.trace_rays(rays)
+    ordr = scene.trace_rays(rays, traversal=pkg.RTB_TRAVERSAL_ORDERED)
+    same = ref["object"] == ordr["object"]
+    assert same.mean() >= 0.9999, f"{(~same).sum()} of {same.size} rays disagree"
+    both = same & (ref["object"] >= 0)
+    assert np.array_equal(ref["t"][both], ordr["t"][both])          # same arithmetic -> same bits
+    assert np.array_equal(ref["front_face"][both], ordr["front_face"][both])
+    bad = ~same & (ref["object"] >= 0) & (ordr["object"] >= 0)
+    if bad.any():  # where they disagree the two candidate roots are within rounding of each other
+        np.testing.assert_allclose(ref["t"][bad], ordr["t"][bad], rtol=1e-4)
+    assert ordr["n_box_tests"].sum() <= ref["n_box_tests"].sum()
+
+
+@pytest.mark.parametrize("integrator", [0, 1])
+def test_ordered_render_matches_reference_order_render(pkg, book1, integrator):
+    """Same Philox streams, ORDERED vs REFERENCE traversal: identical paths except where a hit index differs."""
+    world, scene = book1
+    cam = pkg.book1_camera(200, 4, 50).init()
+    a, _, sa = scene.render(cam, pkg.render_options(seed=21, integrator=integrator, flags=pkg.RTB_FLAG_COUNT_WORK))
+    b, _, sb = scene.render(cam, pkg.render_options(seed=21, integrator=integrator, flags=pkg.RTB_FLAG_COUNT_WORK,
+                                                    traversal=pkg.RTB_TRAVERSAL_ORDERED))
+    diff = np.abs(a[:, :3] - b[:, :3]).max(axis=1)
+    assert np.count_nonzero(diff > 1e-5) <= 1e-3 * diff.shape[0]
+    assert abs(sa["n_rays"] - sb["n_rays"]) <= 1e-3 * sa["n_rays"] and sa["n_paths"] == sb["n_paths"]
+    assert sb["n_box_tests"] <= sa["n_box_tests"]
+
+
+def test_wavefront_multi_batch_pipeline_bit_exact(pkg, book1):
+    """Enough samples for several ~8 M-path batches on several streams: per-pixel sums must still be in sample
+    order, i.e. bit-identical to the megakernel."""
+    world, scene = book1
+    cam = pkg.book1_camera(1200, 36, 50).init()   # 810 000 px x 36 spp = 29 M paths -> 4 batches over 3 lanes
+    a, _, _ = scene.render(cam, pkg.render_options(seed=31, integrator=pkg.RTB_INTEGRATOR_WAVEFRONT))
+    b, _, _ = scene.render(cam, pkg.render_options(seed=31, integrator=pkg.RTB_INTEGRATOR_MEGAKERNEL))
+    assert np.array_equal(a, b)

@@ -19,6 +19,7 @@ ap.add_argument("--n", type=int, default=1000000)
 ap.add_argument("--integrators", default="0,1")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--count", action="store_true")
+ap.add_argument("--traversal", type=int, default=0)
 a = ap.parse_args()
 
 import torch
@@ -37,7 +38,7 @@ acc = torch.zeros(npx, 4, device="cuda")
 for integ in [int(x) for x in a.integrators.split(",")]:
     for rep in range(a.reps):
         acc.zero_()
-        o = p.render_options(seed=1234, integrator=integ, flags=p.RTB_FLAG_COUNT_WORK if a.count else 0)
+        o = p.render_options(seed=1234, integrator=integ, traversal=a.traversal, flags=p.RTB_FLAG_COUNT_WORK if a.count else 0)
         torch.cuda.synchronize()
         st = scene.render_device(cam, o, acc.data_ptr(), 0)
         mp = st["n_paths"] / st["device_ms"] / 1e3
@@ -45,5 +46,5 @@ for integ in [int(x) for x in a.integrators.split(",")]:
         if a.count:
             extra = (f" rays/path={st['n_rays']/st['n_paths']:.2f} box/ray={st['n_box_tests']/st['n_rays']:.1f}"
                      f" obj/ray={st['n_object_tests']/st['n_rays']:.1f} Mrays/s={st['n_rays']/st['device_ms']/1e3:.1f}")
-        print(f"{a.scene} {cam.image_width}x{cam.image_height} spp={a.spp} integrator={integ} rep={rep}: "
+        print(f"{a.scene} {cam.image_width}x{cam.image_height} spp={a.spp} integrator={integ} traversal={a.traversal} rep={rep}: "
               f"{st['device_ms']:.2f} ms, {mp:.1f} Mpaths/s, launches={st['n_launches']}{extra}", flush=True)

@@ -301,6 +301,13 @@ def philox_device(counters: np.ndarray, key, device: int = 0) -> np.ndarray:
     return out
 
 
+def measure_fp32_peak(device: int = 0) -> float:
+    """FFMA microbenchmark, TFLOP/s (FMA = 2 flops)."""
+    v = C.c_double(0.0)
+    _check(_ffi.rtb().rtb_measure_fp32_peak(device, C.byref(v)), "rtb_measure_fp32_peak")
+    return v.value
+
+
 def write_ppm(path: str, rgba: np.ndarray, width: int, height: int) -> None:
     rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
     _check(_ffi.rtw().rtw_write_ppm(path.encode(), rgba.ctypes.data, width, height), "rtw_write_ppm")

@@ -29,7 +29,7 @@ RTB_MAT_LAMBERTIAN, RTB_MAT_METAL, RTB_MAT_DIELECTRIC, RTB_MAT_DIFFUSE_LIGHT, RT
 RTB_TEX_SOLID, RTB_TEX_CHECKER, RTB_TEX_IMAGE, RTB_TEX_NOISE = range(4)
 RTB_BACKGROUND_SOLID, RTB_BACKGROUND_SKY = 0, 1
 RTB_INTEGRATOR_MEGAKERNEL, RTB_INTEGRATOR_WAVEFRONT = 0, 1
-RTB_TRAVERSAL_REFERENCE = 0
+RTB_TRAVERSAL_REFERENCE, RTB_TRAVERSAL_ORDERED = 0, 1
 RTB_FLAG_COUNT_WORK = 1
 
 RTW_SCENE_BOOK1, RTW_SCENE_EARTH, RTW_SCENE_TWO_SPHERES, RTW_SCENE_TWO_PERLIN, RTW_SCENE_TEXTURED, \
@@ -129,6 +129,7 @@ RTB_SYMBOLS = [
     "rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_scene_create", "rtb_scene_destroy",
     "rtb_trace_rays", "rtb_render", "rtb_render_device", "rtb_resolve_device", "rtb_resolve", "rtb_render_async",
     "rtb_job_progress", "rtb_job_cancel", "rtb_job_wait", "rtb_job_destroy", "rtb_philox_device_selftest",
+    "rtb_measure_fp32_peak",
 ]
 RTW_SYMBOLS = [
     "rtw_world_create", "rtw_world_new", "rtw_world_add_image", "rtw_world_add_sphere", "rtw_world_add_quad",
@@ -174,6 +175,7 @@ def rtb() -> C.CDLL:
     lib.rtb_job_wait.argtypes = [vp, C.POINTER(RtbRenderStats)]
     lib.rtb_job_destroy.argtypes = [vp]
     lib.rtb_philox_device_selftest.argtypes = [vp, vp, u32, vp, C.c_int]
+    lib.rtb_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     for s in RTB_SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("rtb_abi_version", "rtb_last_error"):

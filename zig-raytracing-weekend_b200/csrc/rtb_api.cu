@@ -161,29 +161,29 @@ static int validate_desc(const RtbSceneDesc* d) {
     return RTB_OK;
 }
 
-// Pointer graph -> threaded pre-order array.  Iterative (no recursion: the caller's tree may be
-// arbitrarily deep).  Pass 1 computes subtree sizes in post-order, pass 2 assigns pre-order slots:
-// slot(left) = slot + 1, slot(right) = slot + 1 + size(left), skip = slot + size(self).
-static int build_threaded(const RtbSceneDesc* d, std::vector<float4>& out, std::vector<DevQuad>& quads,
-                          uint32_t* depth_out) {
-    out.clear();
+// Pointer graph -> threaded pre-order arrays.  Iterative (no recursion: the caller's tree may be
+// arbitrarily deep).  tree_sizes validates the graph and computes subtree sizes in post-order;
+// emit_layout assigns pre-order slots: slot(first) = slot + 1, slot(second) = slot + 1 + size(first),
+// skip = slot + size(self).
+static int tree_sizes(const RtbSceneDesc* d, std::vector<uint32_t>& size, uint32_t* depth_out) {
     *depth_out = 0;
-    if (d->n_nodes == 0) return RTB_OK;
     const uint32_t n = d->n_nodes;
-    std::vector<uint32_t> size(n, 0);
+    size.assign(n, 0);
+    if (n == 0) return RTB_OK;
     std::vector<uint8_t> state(n, 0);  // 0 = unseen, 1 = expanded, 2 = sized
+    std::vector<uint32_t> depth(n, 0);
     std::vector<int32_t> stack;
     stack.push_back(d->root);
-    uint32_t visited = 0;
+    depth[d->root] = 1;
     while (!stack.empty()) {
         const int32_t i = stack.back();
         const RtbBvhNode& nd = d->nodes[i];
+        if (depth[i] > *depth_out) *depth_out = depth[i];
         if (nd.leaf >= 0) {
             if ((uint32_t)nd.leaf >= d->n_hittables) return fail(RTB_ERR_INVALID_ARGUMENT, "node %d: leaf out of range", i);
             if (state[i] != 0) return fail(RTB_ERR_INVALID_ARGUMENT, "node %d reached twice (not a tree)", i);
             state[i] = 2;
             size[i] = 1;
-            ++visited;
             stack.pop_back();
             continue;
         }
@@ -191,9 +191,9 @@ static int build_threaded(const RtbSceneDesc* d, std::vector<float4>& out, std::
             return fail(RTB_ERR_INVALID_ARGUMENT, "node %d: child out of range", i);
         if (state[i] == 0) {
             state[i] = 1;
-            ++visited;
             if (state[nd.left] != 0 || state[nd.right] != 0 || nd.left == nd.right)
                 return fail(RTB_ERR_INVALID_ARGUMENT, "node %d: child reached twice (not a tree)", i);
+            depth[nd.left] = depth[nd.right] = depth[i] + 1;
             stack.push_back(nd.right);
             stack.push_back(nd.left);
         } else {
@@ -202,41 +202,75 @@ static int build_threaded(const RtbSceneDesc* d, std::vector<float4>& out, std::
             stack.pop_back();
         }
     }
-    const uint32_t total = size[d->root];
-    out.resize(2 * (size_t)total);
+    return RTB_OK;
+}
+
+static void leaf_record(const RtbSceneDesc* d, uint32_t object, const std::vector<uint32_t>& quad_slot, float4* f0,
+                        float4* f1) {
+    const RtbHittable& h = d->hittables[object];
+    if (h.type == RTB_HITTABLE_SPHERE) {
+        const uint32_t kind = h.is_moving ? KIND_MOVING_SPHERE : KIND_SPHERE;
+        *f0 = mkf4(h.a[0], h.a[1], h.a[2], bits((kind << 30) | object));
+        *f1 = mkf4(h.b[0], h.b[1], h.b[2], h.radius);
+    } else {
+        *f0 = mkf4(0, 0, 0, bits((KIND_QUAD << 30) | object));
+        *f1 = mkf4(0, 0, 0, bits(quad_slot[object]));
+    }
+}
+
+// octant < 0: bounds as (min, max), reference child order (megakernel / ray queries).
+// octant 0..7: bounds pre-swapped to (entry, exit) planes for rays with invD<0 on the axes whose bit
+// is set; child order = reference (left first) or, if `ordered`, the child the ray meets first along
+// the axis that separates the two children most (the builder split on box-min order, bvh.zig:64-67).
+static void emit_layout(const RtbSceneDesc* d, const std::vector<uint32_t>& size, const std::vector<uint32_t>& quad_slot,
+                        int octant, bool ordered, float4* out) {
+    if (d->n_nodes == 0) return;
     struct Item {
         int32_t node;
         uint32_t slot;
-        uint32_t depth;
     };
     std::vector<Item> work;
-    work.push_back({d->root, 0u, 1u});
+    work.push_back({d->root, 0u});
     while (!work.empty()) {
         const Item it = work.back();
         work.pop_back();
         const RtbBvhNode& nd = d->nodes[it.node];
-        if (it.depth > *depth_out) *depth_out = it.depth;
         if (nd.leaf >= 0) {
-            const RtbHittable& h = d->hittables[nd.leaf];
-            if (h.type == RTB_HITTABLE_SPHERE) {
-                const uint32_t kind = h.is_moving ? KIND_MOVING_SPHERE : KIND_SPHERE;
-                out[2 * (size_t)it.slot] = mkf4(h.a[0], h.a[1], h.a[2], bits((kind << 30) | (uint32_t)nd.leaf));
-                out[2 * (size_t)it.slot + 1] = mkf4(h.b[0], h.b[1], h.b[2], h.radius);
-            } else {
-                out[2 * (size_t)it.slot] = mkf4(0, 0, 0, bits((KIND_QUAD << 30) | (uint32_t)nd.leaf));
-                out[2 * (size_t)it.slot + 1] = mkf4(0, 0, 0, bits((uint32_t)quads.size()));
-                quads.push_back(make_quad(h));
-            }
-        } else {
-            const uint32_t skip = it.slot + size[it.node];
-            out[2 * (size_t)it.slot] = mkf4(nd.bmin[0], nd.bmin[1], nd.bmin[2], bits((KIND_INTERIOR << 30) | skip));
-            out[2 * (size_t)it.slot + 1] = mkf4(nd.bmax[0], nd.bmax[1], nd.bmax[2], 0.0f);
-            work.push_back({nd.right, it.slot + 1u + size[nd.left], it.depth + 1u});
-            work.push_back({nd.left, it.slot + 1u, it.depth + 1u});
+            leaf_record(d, (uint32_t)nd.leaf, quad_slot, &out[2 * (size_t)it.slot], &out[2 * (size_t)it.slot + 1]);
+            continue;
         }
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            const bool neg = octant >= 0 && ((octant >> a) & 1);
+            lo[a] = neg ? nd.bmax[a] : nd.bmin[a];
+            hi[a] = neg ? nd.bmin[a] : nd.bmax[a];
+        }
+        const uint32_t skip = it.slot + size[it.node];
+        out[2 * (size_t)it.slot] = mkf4(lo[0], lo[1], lo[2], bits((KIND_INTERIOR << 30) | skip));
+        out[2 * (size_t)it.slot + 1] = mkf4(hi[0], hi[1], hi[2], 0.0f);
+        int32_t first = nd.left, second = nd.right;
+        if (ordered && octant >= 0) {
+            const RtbBvhNode& l = d->nodes[nd.left];
+            const RtbBvhNode& r = d->nodes[nd.right];
+            int axis = 0;
+            float best = -1.0f;
+            for (int a = 0; a < 3; ++a) {
+                const float sep = std::fabs((r.bmin[a] + r.bmax[a]) - (l.bmin[a] + l.bmax[a]));
+                if (sep > best) {
+                    best = sep;
+                    axis = a;
+                }
+            }
+            const bool left_is_low = (l.bmin[axis] + l.bmax[axis]) <= (r.bmin[axis] + r.bmax[axis]);
+            const bool dir_negative = ((octant >> axis) & 1) != 0;
+            if (left_is_low == dir_negative) {  // the ray comes from the high side: right child first
+                first = nd.right;
+                second = nd.left;
+            }
+        }
+        work.push_back({second, it.slot + 1u + size[first]});
+        work.push_back({first, it.slot + 1u});
     }
-    (void)visited;
-    return RTB_OK;
 }
 
 static void scene_free(RtbScene* sc) {
@@ -258,11 +292,30 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     if (device < 0 || device >= ndev) return fail(RTB_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, ndev - 1);
     RTB_CUDA(cudaSetDevice(device));
 
-    std::vector<float4> nodes;
-    std::vector<DevQuad> quads;
+    std::vector<uint32_t> size;
     uint32_t depth = 0;
-    rc = build_threaded(desc, nodes, quads, &depth);
+    rc = tree_sizes(desc, size, &depth);
     if (rc != RTB_OK) return rc;
+    std::vector<DevQuad> quads;
+    std::vector<uint32_t> quad_slot(desc->n_hittables, 0);
+    for (uint32_t i = 0; i < desc->n_hittables; ++i) {
+        if (desc->hittables[i].type == RTB_HITTABLE_QUAD) {
+            quad_slot[i] = (uint32_t)quads.size();
+            quads.push_back(make_quad(desc->hittables[i]));
+        }
+    }
+    const uint32_t n_tree = desc->n_nodes ? size[desc->root] : 0u;
+    std::vector<float4> nodes(2 * (size_t)n_tree);
+    emit_layout(desc, size, quad_slot, -1, false, nodes.data());
+    // per-octant layouts, [mode][octant][2 * n_tree]
+    std::vector<float4> oct_nodes[2];
+    for (int mode = 0; mode < 2; ++mode) {
+        oct_nodes[mode].resize(16 * (size_t)n_tree);
+        for (int oct = 0; oct < 8; ++oct)
+            emit_layout(desc, size, quad_slot, oct, mode == 1, oct_nodes[mode].data() + (size_t)oct * 2 * n_tree);
+    }
+    std::vector<float4> prims(2 * (size_t)desc->n_hittables);
+    for (uint32_t i = 0; i < desc->n_hittables; ++i) leaf_record(desc, i, quad_slot, &prims[2 * (size_t)i], &prims[2 * (size_t)i + 1]);
 
     RtbScene* sc = new (std::nothrow) RtbScene();
     if (!sc) return fail(RTB_ERR_OUT_OF_MEMORY, "host allocation failed");
@@ -317,6 +370,9 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
         }
     }
     if (rc == RTB_OK) rc = upload(sc, nodes, &sc->dev.nodes);
+    if (rc == RTB_OK) rc = upload(sc, oct_nodes[0], &sc->dev.oct_nodes[0]);
+    if (rc == RTB_OK) rc = upload(sc, oct_nodes[1], &sc->dev.oct_nodes[1]);
+    if (rc == RTB_OK) rc = upload(sc, prims, &sc->dev.prims);
     if (rc == RTB_OK) rc = upload(sc, obj_mat, &sc->dev.object_material);
     if (rc == RTB_OK) rc = upload(sc, mats, &sc->dev.materials);
     if (rc == RTB_OK) rc = upload(sc, texs, &sc->dev.textures);
@@ -355,7 +411,7 @@ extern "C" int rtb_scene_destroy(RtbScene* scene) {
 extern "C" int rtb_trace_rays(RtbScene* scene, const RtbRay* rays, uint64_t n, uint32_t traversal, RtbHit* hits_out) {
     if (!scene) return fail(RTB_ERR_INVALID_ARGUMENT, "scene is NULL");
     if (n && (!rays || !hits_out)) return fail(RTB_ERR_INVALID_ARGUMENT, "rays/hits_out is NULL");
-    if (traversal != RTB_TRAVERSAL_REFERENCE) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", traversal);
+    if (traversal > RTB_TRAVERSAL_ORDERED) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", traversal);
     if (n == 0) return RTB_OK;
     std::lock_guard<std::mutex> lock(scene->mutex);
     RTB_CUDA(cudaSetDevice(scene->device));
@@ -364,7 +420,7 @@ extern "C" int rtb_trace_rays(RtbScene* scene, const RtbRay* rays, uint64_t n, u
     RTB_CUDA(cudaMalloc(&d_rays, n * sizeof(RtbRay)));
     cudaError_t e = cudaMalloc(&d_hits, n * sizeof(RtbHit));
     if (e == cudaSuccess) e = cudaMemcpy(d_rays, rays, n * sizeof(RtbRay), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_trace(scene->dev, d_rays, n, d_hits, 0);
+    if (e == cudaSuccess) e = launch_trace(scene->dev, d_rays, n, d_hits, traversal == RTB_TRAVERSAL_ORDERED, 0);
     if (e == cudaSuccess) e = cudaMemcpy(hits_out, d_hits, n * sizeof(RtbHit), cudaMemcpyDeviceToHost);
     cudaFree(d_rays);
     cudaFree(d_hits);
@@ -399,7 +455,7 @@ static int check_render_args(RtbScene* scene, const RtbCamera* cam, const RtbRen
     if (opt->tile_world > 0 && opt->tile_rank >= opt->tile_world) return fail(RTB_ERR_INVALID_ARGUMENT, "tile_rank >= tile_world");
     if (opt->integrator != RTB_INTEGRATOR_MEGAKERNEL && opt->integrator != RTB_INTEGRATOR_WAVEFRONT)
         return fail(RTB_ERR_INVALID_ARGUMENT, "unknown integrator %u", opt->integrator);
-    if (opt->traversal != RTB_TRAVERSAL_REFERENCE) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", opt->traversal);
+    if (opt->traversal > RTB_TRAVERSAL_ORDERED) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", opt->traversal);
     if (cam->background_mode > RTB_BACKGROUND_SKY) return fail(RTB_ERR_INVALID_ARGUMENT, "unknown background mode");
     return RTB_OK;
 }
@@ -419,6 +475,7 @@ static int render_enqueue(RtbScene* scene, const RtbCamera* cam, const RtbRender
     p.pixel_end = (opt->pixel_begin == 0 && opt->pixel_count == 0) ? size : opt->pixel_begin + opt->pixel_count;
     p.tile_rank = opt->tile_rank;
     p.tile_world = opt->tile_world ? opt->tile_world : 1u;
+    p.ordered = opt->traversal == RTB_TRAVERSAL_ORDERED ? 1u : 0u;
     const bool count_work = (opt->flags & RTB_FLAG_COUNT_WORK) != 0;
     p.counters = count_work ? scene->d_counters : nullptr;
     if (opt->integrator == RTB_INTEGRATOR_WAVEFRONT) {
@@ -680,5 +737,41 @@ extern "C" int rtb_philox_device_selftest(const uint32_t* counters4, const uint3
     cudaFree(d_in);
     cudaFree(d_out);
     if (e != cudaSuccess) return cuda_fail(e, "rtb_philox_device_selftest");
+    return RTB_OK;
+}
+
+// ------------------------------------------------------------------ FP32 peak (roofline denominator)
+extern "C" int rtb_measure_fp32_peak(int device, double* tflops_out) {
+    if (!tflops_out) return fail(RTB_ERR_INVALID_ARGUMENT, "tflops_out is NULL");
+    int ndev = 0;
+    int rc = rtb_device_count(&ndev);
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RTB_CUDA(cudaGetDeviceProperties(&prop, device));
+    const uint32_t grid = (uint32_t)prop.multiProcessorCount * 8u;
+    const uint32_t iters = 1u << 15;
+    float* d_out = nullptr;
+    RTB_CUDA(cudaMalloc(&d_out, (size_t)grid * 256 * sizeof(float)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 6 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(e0, 0);
+        e = launch_ffma_peak(d_out, grid, iters, 0);
+        cudaEventRecord(e1, 0);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = (double)grid * 256.0 * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;  // rep 0 is the warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "rtb_measure_fp32_peak");
+    *tflops_out = best;
     return RTB_OK;
 }

@@ -54,7 +54,11 @@ struct DevQuad {  // Quad fields incl. the ones Quad.init derives (src/objects.z
 };
 
 struct DevScene {
-    const float4* nodes;  // 2 per node
+    const float4* nodes;  // 2 per node: reference order, bounds as (min, max)
+    // Per-octant layouts for the wavefront integrator, [mode][octant][2 * n_nodes], bounds pre-swapped
+    // to (entry plane, exit plane) for the octant.  mode 0 = reference order, 1 = near-child-first.
+    const float4* oct_nodes[2];
+    const float4* prims;  // 2 per object: the leaf record {center1, kind|object}, {center_vec, radius}
     uint32_t n_nodes;
     uint32_t n_objects;
     const uint32_t* object_material;  // object index -> material index
@@ -210,6 +214,126 @@ __device__ __forceinline__ bool quad_root(const DRay& r, const DevQuad& qd, floa
     return true;
 }
 
+// 3-input min/max (sm_100a FMNMX3).  PTX min/max return the non-NaN operand, which is exactly
+// what the reference's `if (t0 > ray_t_min) ray_t_min = t0` does with a NaN t0: nothing.
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// Aabb.hit (src/aabb.zig:82-114) == false.  f0.xyz = box min, f1.xyz = box max.
+//   * 1/direction is hoisted out of the node loop (the reference recomputes the same IEEE quotient
+//     at every node);
+//   * the swap `if (invD < 0)` is a select on the per-ray sign;
+//   * `if (t0 > tmin) tmin = t0` / `if (t1 < tmax) tmax = t1` are max/min that ignore a NaN t (the
+//     running tmin/tmax are never NaN), and the three per-axis early-outs fold into one final
+//     `tmax <= tmin`, which is equivalent because tmin only grows and tmax only shrinks.
+__device__ __forceinline__ bool slab_miss(float4 f0, float4 f1, float3 o, float inv_x, float inv_y, float inv_z,
+                                          float t_min, float t_max) {
+    const float ax = (f0.x - o.x) * inv_x, bx = (f1.x - o.x) * inv_x;
+    const float ay = (f0.y - o.y) * inv_y, by = (f1.y - o.y) * inv_y;
+    const float az = (f0.z - o.z) * inv_z, bz = (f1.z - o.z) * inv_z;
+    const bool sx = inv_x < 0.0f, sy = inv_y < 0.0f, sz = inv_z < 0.0f;
+    const float t0x = sx ? bx : ax, t1x = sx ? ax : bx;
+    const float t0y = sy ? by : ay, t1y = sy ? ay : by;
+    const float t0z = sz ? bz : az, t1z = sz ? az : bz;
+    const float lo = fmaxf(max3f(t0x, t0y, t0z), t_min);
+    const float hi = fminf(min3f(t1x, t1y, t1z), t_max);
+    return hi <= lo;
+}
+
+// Octant of a ray = the three `invD < 0` predicates of Aabb.hit (src/aabb.zig:97), bit k = axis k.
+__device__ __forceinline__ uint32_t ray_octant(float inv_x, float inv_y, float inv_z) {
+    return (inv_x < 0.0f ? 1u : 0u) | (inv_y < 0.0f ? 2u : 0u) | (inv_z < 0.0f ? 4u : 0u);
+}
+
+// Slab test against a node of a PER-OCTANT layout: f0.xyz already holds the plane the ray enters
+// through on each axis (min, or max where invD < 0) and f1.xyz the one it leaves through, so the
+// reference's swap is done once per (node, octant) on the host instead of per visit.  The values
+// t0/t1 are the same IEEE results as in slab_miss.
+__device__ __forceinline__ bool slab_miss_preswapped(float4 f0, float4 f1, float3 o, float inv_x, float inv_y,
+                                                     float inv_z, float t_min, float t_max) {
+    const float t0x = (f0.x - o.x) * inv_x, t1x = (f1.x - o.x) * inv_x;
+    const float t0y = (f0.y - o.y) * inv_y, t1y = (f1.y - o.y) * inv_y;
+    const float t0z = (f0.z - o.z) * inv_z, t1z = (f1.z - o.z) * inv_z;
+    const float lo = fmaxf(max3f(t0x, t0y, t0z), t_min);
+    const float hi = fminf(min3f(t1x, t1y, t1z), t_max);
+    return hi <= lo;
+}
+
+// Sphere.hit up to the accepted root with a = |direction|^2 hoisted out of the node loop (the
+// reference recomputes the same value at every leaf, src/objects.zig:124).
+__device__ __forceinline__ bool sphere_root_a(float3 o, float3 d, float a, float3 center, float radius, float t_min,
+                                              float t_max, float& root_out) {
+    const float3 oc = o - center;
+    const float half_b = dot3(oc, d);
+    const float c = length_squared(oc) - radius * radius;
+    const float discriminant = half_b * half_b - a * c;
+    if (discriminant < 0.0f) return false;
+    const float sqrtd = sqrtf(discriminant);
+    float root = (-half_b - sqrtd) / a;
+    if (!(t_min < root && root < t_max)) {
+        root = (-half_b + sqrtd) / a;
+        if (!(t_min < root && root < t_max)) return false;
+    }
+    root_out = root;
+    return true;
+}
+
+// Traversal over one octant's threaded layout (DevScene::oct_nodes).  Visiting order is whatever the
+// host baked into the layout: the reference's left-then-right order (RTB_TRAVERSAL_REFERENCE) or
+// near-child-first for this octant (RTB_TRAVERSAL_ORDERED).  Nearest.node is the OBJECT index.
+template <bool COUNT, bool QUADS>
+__device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ nodes, uint32_t n_nodes,
+                                                   const DevQuad* __restrict__ quads, float3 o, float3 d, float time,
+                                                   float inv_x, float inv_y, float inv_z, float t_min, float t_max,
+                                                   uint32_t& n_box, uint32_t& n_obj) {
+    Nearest best;
+    best.t = t_max;
+    best.node = 0xffffffffu;
+    const float a = length_squared(d);
+    uint32_t i = 0;
+    while (i < n_nodes) {
+        const float4 f0 = nodes[2u * i];
+        const float4 f1 = nodes[2u * i + 1u];
+        const uint32_t meta = __float_as_uint(f0.w);
+        if (meta < (1u << 30)) {  // KIND_INTERIOR: meta is the skip index
+            if (COUNT) ++n_box;
+            i = slab_miss_preswapped(f0, f1, o, inv_x, inv_y, inv_z, t_min, best.t) ? meta : i + 1u;
+        } else {
+            if (COUNT) ++n_obj;
+            const uint32_t kind = meta >> 30;
+            if (!QUADS || kind != KIND_QUAD) {
+                const float3 c1 = f3(f0);
+                const float3 center = (kind == KIND_MOVING_SPHERE) ? c1 + splat3(time) * f3(f1) : c1;
+                float root;
+                if (sphere_root_a(o, d, a, center, f1.w, t_min, best.t, root)) {
+                    best.t = root;
+                    best.node = meta & RTB_META_INDEX_MASK;
+                }
+            } else {
+                DRay r;
+                r.o = o;
+                r.d = d;
+                r.time = time;
+                float t, alpha, beta;
+                if (quad_root(r, quads[__float_as_uint(f1.w)], t_min, best.t, t, alpha, beta)) {
+                    best.t = t;
+                    best.node = meta & RTB_META_INDEX_MASK;
+                }
+            }
+            i = i + 1u;
+        }
+    }
+    return best;
+}
+
 // BVHTree.hit in the reference's visiting order (src/bvh.zig:122-136) over the threaded layout.
 //   * interior node: Aabb.hit with ray_t = (t_min, closest so far)  (src/aabb.zig:82-114);
 //     1/direction is hoisted out of the loop (the reference recomputes the same IEEE quotient at
@@ -234,20 +358,7 @@ __device__ __forceinline__ Nearest traverse_reference(const float4* __restrict__
         const uint32_t kind = meta >> 30;
         if (kind == KIND_INTERIOR) {
             if (COUNT) ++n_box;
-            float t0x = (f0.x - r.o.x) * inv_x, t1x = (f1.x - r.o.x) * inv_x;
-            float t0y = (f0.y - r.o.y) * inv_y, t1y = (f1.y - r.o.y) * inv_y;
-            float t0z = (f0.z - r.o.z) * inv_z, t1z = (f1.z - r.o.z) * inv_z;
-            if (inv_x < 0.0f) { const float s = t0x; t0x = t1x; t1x = s; }
-            if (inv_y < 0.0f) { const float s = t0y; t0y = t1y; t1y = s; }
-            if (inv_z < 0.0f) { const float s = t0z; t0z = t1z; t1z = s; }
-            float lo = t_min, hi = best.t;
-            if (t0x > lo) lo = t0x;
-            if (t1x < hi) hi = t1x;
-            if (t0y > lo) lo = t0y;
-            if (t1y < hi) hi = t1y;
-            if (t0z > lo) lo = t0z;
-            if (t1z < hi) hi = t1z;
-            i = (hi <= lo) ? (meta & RTB_META_INDEX_MASK) : i + 1u;
+            i = slab_miss(f0, f1, r.o, inv_x, inv_y, inv_z, t_min, best.t) ? (meta & RTB_META_INDEX_MASK) : i + 1u;
         } else {
             if (COUNT) ++n_obj;
             if (!QUADS || kind != KIND_QUAD) {

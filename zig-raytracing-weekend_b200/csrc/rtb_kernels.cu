@@ -17,15 +17,18 @@ namespace rtb {
 // starts its next sample at once, so the warp stays converged on the traversal loop instead of
 // idling until its longest path finishes.
 // ------------------------------------------------------------------------------------------
-template <bool SMEM_NODES, bool COUNT, bool QUADS>
+// ORDERED: near-child-first per-octant layouts read from global memory (8 layouts do not fit in shared
+// memory); Nearest.node is then an object index and the leaf records come from scene.prims.
+template <bool SMEM_NODES, bool COUNT, bool QUADS, bool ORDERED>
 __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderParams P) {
     extern __shared__ float4 s_nodes[];
     const float4* __restrict__ nodes = P.scene.nodes;
-    if (SMEM_NODES) {
+    if (SMEM_NODES && !ORDERED) {
         for (uint32_t i = threadIdx.x; i < 2u * P.scene.n_nodes; i += kCtaThreads) s_nodes[i] = P.scene.nodes[i];
         __syncthreads();
         nodes = s_nodes;
     }
+    const float4* __restrict__ leaves = ORDERED ? P.scene.prims : nodes;
 
     const uint32_t tiles_x = (P.cam.width + kTileW - 1u) / kTileW;
     const uint32_t tile = blockIdx.x * P.tile_world + P.tile_rank;
@@ -50,15 +53,23 @@ __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderPar
             uint32_t segment = 1u;
             for (;;) {
                 if (COUNT) ++n_rays;
-                const Nearest best = traverse_reference<COUNT, QUADS>(nodes, P.scene.n_nodes, P.scene.quads, ray,
-                                                                      0.001f, __int_as_float(0x7f800000), n_box, n_obj);
+                Nearest best;
+                if (ORDERED) {
+                    const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
+                    const float4* oct = P.scene.oct_nodes[1] + (size_t)ray_octant(ix, iy, iz) * 2u * P.scene.n_nodes;
+                    best = traverse_octant<COUNT, QUADS>(oct, P.scene.n_nodes, P.scene.quads, ray.o, ray.d, ray.time, ix,
+                                                         iy, iz, 0.001f, __int_as_float(0x7f800000), n_box, n_obj);
+                } else {
+                    best = traverse_reference<COUNT, QUADS>(nodes, P.scene.n_nodes, P.scene.quads, ray, 0.001f,
+                                                            __int_as_float(0x7f800000), n_box, n_obj);
+                }
                 bool done;
                 if (best.node == 0xffffffffu) {
                     L = L + T * miss_color(P.cam, ray);
                     done = true;
                 } else {
                     if (COUNT) ++n_hits;
-                    const ShadeResult sr = shade<QUADS>(P.scene, nodes, ray, best, key, segment);
+                    const ShadeResult sr = shade<QUADS>(P.scene, leaves, ray, best, key, segment);
                     L = L + T * sr.emitted;
                     if (sr.scatters && segment < P.cam.max_depth) {
                         T = T * sr.attenuation;
@@ -95,9 +106,9 @@ __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderPar
     }
 }
 
-template <bool SMEM, bool COUNT, bool QUADS>
+template <bool SMEM, bool COUNT, bool QUADS, bool ORDERED = false>
 static cudaError_t launch_mega_variant(const RenderParams& p, uint32_t grid, size_t smem, cudaStream_t stream) {
-    auto kernel = render_megakernel<SMEM, COUNT, QUADS>;
+    auto kernel = render_megakernel<SMEM, COUNT, QUADS, ORDERED>;
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -122,6 +133,14 @@ cudaError_t launch_megakernel(const RenderParams& p, bool nodes_in_smem, bool co
     const size_t smem = nodes_in_smem ? (size_t)p.scene.n_nodes * 32u : 0u;
     const bool quads = p.scene.has_quads != 0u;
     cudaError_t e;
+    if (p.ordered) {
+        if (count_work) e = quads ? launch_mega_variant<false, true, true, true>(q, grid, 0, stream)
+                                  : launch_mega_variant<false, true, false, true>(q, grid, 0, stream);
+        else            e = quads ? launch_mega_variant<false, false, true, true>(q, grid, 0, stream)
+                                  : launch_mega_variant<false, false, false, true>(q, grid, 0, stream);
+        if (e == cudaSuccess && info) info->n_launches += 1;
+        return e;
+    }
 #define RTB_DISPATCH(S, C, Q) e = launch_mega_variant<S, C, Q>(q, grid, smem, stream)
     if (nodes_in_smem) {
         if (count_work) { if (quads) RTB_DISPATCH(true, true, true); else RTB_DISPATCH(true, true, false); }
@@ -138,7 +157,7 @@ cudaError_t launch_megakernel(const RenderParams& p, bool nodes_in_smem, bool co
 // ------------------------------------------------------------------------------------------
 // K3 — ray queries.  One thread per ray, reference visiting order, full HitRecord.
 // ------------------------------------------------------------------------------------------
-template <bool QUADS>
+template <bool QUADS, bool ORDERED>
 __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const RtbRay* __restrict__ rays, uint64_t n,
                                                     RtbHit* __restrict__ hits) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,8 +168,16 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     r.d = f3(rr.direction[0], rr.direction[1], rr.direction[2]);
     r.time = rr.time;
     uint32_t n_box = 0, n_obj = 0;
-    const Nearest best =
-        traverse_reference<true, QUADS>(scene.nodes, scene.n_nodes, scene.quads, r, rr.t_min, rr.t_max, n_box, n_obj);
+    Nearest best;
+    if (ORDERED) {
+        const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
+        const float4* oct = scene.oct_nodes[1] + (size_t)ray_octant(ix, iy, iz) * 2u * scene.n_nodes;
+        best = traverse_octant<true, QUADS>(oct, scene.n_nodes, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min,
+                                            rr.t_max, n_box, n_obj);
+    } else {
+        best = traverse_reference<true, QUADS>(scene.nodes, scene.n_nodes, scene.quads, r, rr.t_min, rr.t_max, n_box,
+                                               n_obj);
+    }
     RtbHit h;
     h.object = -1;
     h.front_face = 0u;
@@ -159,7 +186,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     h.normal[0] = h.normal[1] = h.normal[2] = 0.0f;
     h.u = h.v = 0.0f;
     if (best.node != 0xffffffffu) {
-        const DHit d = finish_hit<QUADS, true>(scene.nodes, scene.quads, r, best);
+        const DHit d = finish_hit<QUADS, true>(ORDERED ? scene.prims : scene.nodes, scene.quads, r, best);
         h.object = (int32_t)d.object;
         h.front_face = d.front_face ? 1u : 0u;
         h.t = d.t;
@@ -173,14 +200,17 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     hits[i] = h;
 }
 
-cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n, RtbHit* d_hits,
+cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n, RtbHit* d_hits, bool ordered,
                          cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const uint32_t grid = (uint32_t)((n + 255u) / 256u);
-    if (scene.has_quads)
-        trace_kernel<true><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
-    else
-        trace_kernel<false><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
+    if (scene.has_quads) {
+        if (ordered) trace_kernel<true, true><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
+        else         trace_kernel<true, false><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
+    } else {
+        if (ordered) trace_kernel<false, true><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
+        else         trace_kernel<false, false><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
+    }
     return cudaGetLastError();
 }
 
@@ -213,6 +243,23 @@ __global__ void philox_selftest_kernel(const uint4* __restrict__ ctr, uint2 key,
 cudaError_t launch_philox_selftest(const uint4* d_ctr, uint2 key, uint32_t n, uint4* d_out, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     philox_selftest_kernel<<<(n + 127u) / 128u, 128, 0, stream>>>(d_ctr, key, n, d_out);
+    return cudaGetLastError();
+}
+
+// FP32 FMA peak: 8 independent dependent chains per thread, 3-register FFMA.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* __restrict__ out, uint32_t iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 1.0f + blockIdx.x * 1e-9f, c = 1e-7f * (float)(threadIdx.x & 3u);
+    for (uint32_t i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+        a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+cudaError_t launch_ffma_peak(float* d_out, uint32_t grid, uint32_t iters, cudaStream_t stream) {
+    ffma_peak_kernel<<<grid, 256, 0, stream>>>(d_out, iters);
     return cudaGetLastError();
 }
 

@@ -18,6 +18,7 @@ struct RenderParams {
     uint32_t sample_begin, sample_count;
     uint32_t pixel_begin, pixel_end;  // flat pixel range [begin, end)
     uint32_t tile_rank, tile_world;
+    uint32_t ordered;  // 0 = RTB_TRAVERSAL_REFERENCE, 1 = RTB_TRAVERSAL_ORDERED
     unsigned long long* counters;  // [rays, box tests, object tests, hits] or nullptr
 };
 
@@ -31,7 +32,7 @@ cudaError_t launch_megakernel(const RenderParams& p, bool nodes_in_smem, bool co
                               LaunchInfo* info);
 
 // K3: nearest-hit query for a batch of rays (parity harness).
-cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n, RtbHit* d_hits,
+cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n, RtbHit* d_hits, bool ordered,
                          cudaStream_t stream);
 
 // K4: resolve (toGamma2 + truncation).
@@ -39,6 +40,9 @@ cudaError_t launch_resolve(const float4* d_accum, uchar4* d_rgba, uint64_t n_pix
                            cudaStream_t stream);
 
 cudaError_t launch_philox_selftest(const uint4* d_ctr, uint2 key, uint32_t n, uint4* d_out, cudaStream_t stream);
+
+// FFMA-chain microbenchmark (roofline denominator): out must hold grid*256 floats.
+cudaError_t launch_ffma_peak(float* d_out, uint32_t grid, uint32_t iters, cudaStream_t stream);
 
 // Largest dynamic shared memory the megakernel may use for the node array.
 size_t megakernel_max_smem_nodes_bytes();
