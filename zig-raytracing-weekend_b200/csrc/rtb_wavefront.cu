@@ -17,8 +17,9 @@
 // stage THAT octant's node layout in shared memory, in which every slab is already stored as (entry
 // plane, exit plane): the reference's per-visit swap `if (invD < 0)` (6 FSEL + 3 FSETP) disappears,
 // and the layout may also bake in near-child-first order (RTB_TRAVERSAL_ORDERED) while staying a
-// stackless skip-link walk.  A persistent "refill + leaf-batching" variant of the kernel was also
-// measured and lost to this plain one-thread-per-ray loop, so it is not kept.
+// stackless skip-link walk.  Three persistent variants of the kernel (per-lane refill from the queue,
+// with and without leaf batching / while-while) were measured on B200 and all lost to this plain
+// one-thread-per-ray loop, so they are not kept.
 #include "rtb_wavefront.cuh"
 
 #include <new>
