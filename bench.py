@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--integrator", default="auto", choices=["auto", "megakernel", "wavefront"])
+    ap.add_argument("--traversal", default="reference", choices=["reference", "ordered"],
+                    help="reference = the reference's left-then-right order (bit-exact hit index); ordered = near child first")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--depth", type=int, default=DEPTH)
@@ -164,7 +166,7 @@ def run_reference(a):
 def workload_config(a, cam, integrator):
     return {"workload": f"book1 (generateWorld, ~485 spheres + BVH) {cam.image_width}x{cam.image_height}, "
                         f"{a.spp} spp per GPU, depth {a.depth} [BASELINE configs[1]]",
-            "scene_seed": 1, "bvh_seed": 2, "render_seed": SEED, "integrator": integrator,
+            "scene_seed": 1, "bvh_seed": 2, "render_seed": SEED, "integrator": integrator, "traversal": a.traversal,
             "partition": a.partition if a.gpus > 1 else "none", "background": "sky gradient (camera.zig:204-206)",
             "l2": "flushed between steps (256 MiB memset); scene is 47 KB and cache/smem resident by nature"}
 
@@ -205,15 +207,18 @@ def run_ours(a):
     d_rgba = torch.zeros(npx, 4, device=dev, dtype=torch.uint8)
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 
-    def make_options(step, integrator, flags=0, spp=None):
+    traversal = p.RTB_TRAVERSAL_ORDERED if a.traversal == "ordered" else p.RTB_TRAVERSAL_REFERENCE
+
+    def make_options(step, integrator, flags=0, spp=None, trav=None):
         part = mg.plan(a.partition, rank, world_size, spp or a.spp, sample_base=0,
                        weak=(a.partition == "samples"))
-        o = p.render_options(seed=SEED + step, integrator=integrator, flags=flags)
+        o = p.render_options(seed=SEED + step, integrator=integrator, flags=flags,
+                             traversal=traversal if trav is None else trav)
         return mg.apply(part, o), part
 
-    def step_device(step, integrator, count=False, spp=None):
+    def step_device(step, integrator, count=False, spp=None, trav=None):
         """One device-resident step: clear, render, (reduce), resolve.  Returns this rank's render stats."""
-        o, part = make_options(step, integrator, p.RTB_FLAG_COUNT_WORK if count else 0, spp)
+        o, part = make_options(step, integrator, p.RTB_FLAG_COUNT_WORK if count else 0, spp, trav)
         d_acc.zero_()
         st = scene.render_device(cam, o, d_acc.data_ptr(), sptr, want_stats=count)
         mg.combine(d_acc, part, fix_w=False)
@@ -299,6 +304,20 @@ def run_ours(a):
     # launches per step: one counting-free render reports them
     st1 = scene.render_device(cam, make_options(0, integrator, spp=a.spp)[0], d_acc.data_ptr(), sptr, want_stats=True)
     launches = (st1["n_launches"] + (1 if rank == 0 else 0)) * a.steps
+
+    # -- the other variants, one untimed-for-the-headline step each (evidence for the choice; device-resident) ----
+    variants = {}
+    for vname, vint, vtrav in (("megakernel/reference", p.RTB_INTEGRATOR_MEGAKERNEL, p.RTB_TRAVERSAL_REFERENCE),
+                               ("megakernel/ordered", p.RTB_INTEGRATOR_MEGAKERNEL, p.RTB_TRAVERSAL_ORDERED),
+                               ("wavefront/reference", p.RTB_INTEGRATOR_WAVEFRONT, p.RTB_TRAVERSAL_REFERENCE),
+                               ("wavefront/ordered", p.RTB_INTEGRATOR_WAVEFRONT, p.RTB_TRAVERSAL_ORDERED)):
+        vspp = max(1, min(a.spp, 100))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_device(0, vint, spp=vspp, trav=vtrav)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        variants[vname] = npx * vspp * (world_size if a.partition == "samples" else 1) / (e0.elapsed_time(e1) * 1e-3) / 1e6
 
     # -- e2e: reference-facing call with HOST buffers (pinned), copies inside the timed region ------------------
     e2e = None
@@ -391,7 +410,7 @@ def run_ours(a):
         "config": workload_config(a, cam, integ_name),
         "mrays_per_s": value * cst["n_rays"] / cst["n_paths"],
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "integrator_probe": probe,
+        "integrator_probe": probe, "variants_mpaths_per_s": variants,
     }
     print(json.dumps(out))
     if world_size > 1:
