@@ -52,6 +52,10 @@ struct RtbScene {
     std::vector<void*> allocations;
     bool nodes_fit_smem = false;
     unsigned long long* d_counters = nullptr;
+    // frame-sized staging buffers of the host-buffer entry points, kept across calls
+    float* stage_accum = nullptr;
+    uint8_t* stage_rgba = nullptr;
+    uint64_t stage_pixels = 0;
     WavefrontState* wavefront = nullptr;
     std::mutex mutex;  // serialises renders on one scene (counters / wavefront queues are shared)
 };
@@ -278,6 +282,8 @@ static void scene_free(RtbScene* sc) {
     cudaSetDevice(sc->device);
     if (sc->wavefront) wavefront_destroy(sc->wavefront);
     for (void* p : sc->allocations) cudaFree(p);
+    cudaFree(sc->stage_accum);
+    cudaFree(sc->stage_rgba);
     delete sc;
 }
 
@@ -592,16 +598,20 @@ static int render_host(RtbScene* scene, const RtbCamera* cam, const RtbRenderOpt
     std::lock_guard<std::mutex> lock(scene->mutex);
     RTB_CUDA(cudaSetDevice(scene->device));
     const uint64_t npx = (uint64_t)cam->image_width * cam->image_height;
-    float* d_acc = nullptr;
-    uint8_t* d_rgba = nullptr;
-    RTB_CUDA(cudaMalloc(&d_acc, npx * 16));
-    cudaError_t e = rgba ? cudaMalloc(&d_rgba, npx * 4) : cudaSuccess;
-    if (e == cudaSuccess) e = cudaMemcpy(d_acc, accum, npx * 16, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        cudaFree(d_acc);
-        cudaFree(d_rgba);
-        return cuda_fail(e, "rtb_render upload");
+    if (scene->stage_pixels < npx) {  // (re)size the staging buffers; they live as long as the scene
+        cudaFree(scene->stage_accum);
+        cudaFree(scene->stage_rgba);
+        scene->stage_accum = nullptr;
+        scene->stage_rgba = nullptr;
+        scene->stage_pixels = 0;
+        RTB_CUDA(cudaMalloc(&scene->stage_accum, npx * 16));
+        RTB_CUDA(cudaMalloc(&scene->stage_rgba, npx * 4));
+        scene->stage_pixels = npx;
     }
+    float* d_acc = scene->stage_accum;
+    uint8_t* d_rgba = rgba ? scene->stage_rgba : nullptr;
+    cudaError_t e = cudaMemcpy(d_acc, accum, npx * 16, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "rtb_render upload");
     const uint32_t total = opt->sample_count ? opt->sample_count : cam->samples_per_pixel;
     const uint32_t per_batch = opt->samples_per_launch ? opt->samples_per_launch : total;
     RtbRenderStats acc_stats{};
@@ -648,8 +658,6 @@ static int render_host(RtbScene* scene, const RtbCamera* cam, const RtbRenderOpt
             }
         }
     }
-    cudaFree(d_acc);
-    cudaFree(d_rgba);
     if (stats) *stats = acc_stats;
     if (rc == RTB_OK && cancelled) return fail(RTB_ERR_CANCELLED, "render cancelled");
     return rc;
