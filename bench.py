@@ -420,4 +420,21 @@ def run_ours(a):
 
 if __name__ == "__main__":
     args = parse_args()
-    sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
+    # Contract: rank 0 prints ONE JSON line on stdout.  Libraries (NCCL's version banner, make) also write to fd 1,
+    # so everything but the final line is routed to stderr at the file-descriptor level.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    captured = io.StringIO()
+    py_stdout, sys.stdout = sys.stdout, captured
+    try:
+        rc = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout = py_stdout
+    lines = [ln for ln in captured.getvalue().splitlines() if ln.strip()]
+    for ln in lines[:-1]:
+        print(ln, file=sys.stderr)
+    if lines:
+        os.write(real_stdout, (lines[-1] + "\n").encode())
+    sys.exit(rc)

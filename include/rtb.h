@@ -199,7 +199,13 @@ enum {
      * hits are found earlier and more subtrees are culled.  The nearest hit can differ from the
      * reference's only where float rounding puts a sphere's root on the other side of its own box
      * (measured: tests/test_gpu_parity.py::test_ordered_traversal_agrees). */
-    RTB_TRAVERSAL_ORDERED = 1
+    RTB_TRAVERSAL_ORDERED = 1,
+    /* The library re-partitions the SAME objects (same bounding boxes, one object per leaf) with a
+     * binned surface-area-heuristic tree instead of walking the host's random-axis median-split tree
+     * (src/bvh.zig:48-67), and visits the near child first.  Slab test, primitive test and every hit
+     * value are computed by the same code; only the set of visited nodes changes, so the same caveat
+     * as ORDERED applies.  Not used by the hit-query parity harness unless asked for. */
+    RTB_TRAVERSAL_SAH = 2
 };
 
 enum {

@@ -29,7 +29,7 @@ RTB_MAT_LAMBERTIAN, RTB_MAT_METAL, RTB_MAT_DIELECTRIC, RTB_MAT_DIFFUSE_LIGHT, RT
 RTB_TEX_SOLID, RTB_TEX_CHECKER, RTB_TEX_IMAGE, RTB_TEX_NOISE = range(4)
 RTB_BACKGROUND_SOLID, RTB_BACKGROUND_SKY = 0, 1
 RTB_INTEGRATOR_MEGAKERNEL, RTB_INTEGRATOR_WAVEFRONT = 0, 1
-RTB_TRAVERSAL_REFERENCE, RTB_TRAVERSAL_ORDERED = 0, 1
+RTB_TRAVERSAL_REFERENCE, RTB_TRAVERSAL_ORDERED, RTB_TRAVERSAL_SAH = 0, 1, 2
 RTB_FLAG_COUNT_WORK = 1
 
 RTW_SCENE_BOOK1, RTW_SCENE_EARTH, RTW_SCENE_TWO_SPHERES, RTW_SCENE_TWO_PERLIN, RTW_SCENE_TEXTURED, \

@@ -4,6 +4,7 @@
 // packed materials/textures), owns device memory behind the opaque handles, launches the kernels
 // of rtb_kernels.cu and maps CUDA errors to RtbStatus.  There is NO CPU fallback: without a CUDA
 // device every compute entry point fails with RTB_ERR_NO_DEVICE.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -277,6 +278,147 @@ static void emit_layout(const RtbSceneDesc* d, const std::vector<uint32_t>& size
     }
 }
 
+// RTB_TRAVERSAL_SAH: re-partition the SAME objects (with the bounding boxes the host computed for them)
+// by a binned surface-area-heuristic sweep.  The reference's constructTree picks a random axis and
+// splits at the median (src/bvh.zig:48-67), which on Book-1 costs 50 slab tests per ray and on the
+// 1 M-sphere scene 774; this tree only changes WHICH nodes are visited — slab test, sphere test and
+// every hit value are computed by the same code.  One object per leaf, so it has the same 2n-1 nodes.
+static int32_t build_sah(const RtbSceneDesc* d, const std::vector<uint32_t>& reachable, std::vector<RtbBvhNode>& out) {
+    struct Item {
+        float bmin[3], bmax[3], c[3];
+        int32_t object;
+    };
+    std::vector<Item> items;
+    items.reserve(d->n_hittables);
+    for (uint32_t i = 0; i < d->n_nodes; ++i) {
+        const RtbBvhNode& nd = d->nodes[i];
+        if (nd.leaf < 0 || reachable[i] == 0) continue;  // only what the host's tree actually references
+        Item it;
+        for (int a = 0; a < 3; ++a) {
+            it.bmin[a] = nd.bmin[a];
+            it.bmax[a] = nd.bmax[a];
+            it.c[a] = 0.5f * (nd.bmin[a] + nd.bmax[a]);
+        }
+        it.object = nd.leaf;
+        items.push_back(it);
+    }
+    out.clear();
+    if (items.empty()) return -1;
+    out.reserve(2 * items.size());
+    struct Task {
+        uint32_t lo, hi;
+        int32_t parent;
+        bool is_right;
+    };
+    constexpr int kBins = 16;
+    auto area = [](const float* mn, const float* mx) {
+        const double x = (double)mx[0] - mn[0], y = (double)mx[1] - mn[1], z = (double)mx[2] - mn[2];
+        return x * y + y * z + z * x;
+    };
+    std::vector<Task> stack;
+    stack.push_back({0u, (uint32_t)items.size(), -1, false});
+    while (!stack.empty()) {
+        const Task t = stack.back();
+        stack.pop_back();
+        const int32_t me = (int32_t)out.size();
+        RtbBvhNode nd{};
+        float cmin[3], cmax[3];
+        for (int a = 0; a < 3; ++a) {
+            nd.bmin[a] = cmin[a] = INFINITY;
+            nd.bmax[a] = cmax[a] = -INFINITY;
+        }
+        for (uint32_t i = t.lo; i < t.hi; ++i)
+            for (int a = 0; a < 3; ++a) {
+                nd.bmin[a] = std::fmin(nd.bmin[a], items[i].bmin[a]);
+                nd.bmax[a] = std::fmax(nd.bmax[a], items[i].bmax[a]);
+                cmin[a] = std::fmin(cmin[a], items[i].c[a]);
+                cmax[a] = std::fmax(cmax[a], items[i].c[a]);
+            }
+        nd.left = nd.right = -1;
+        nd.leaf = -1;
+        if (t.parent >= 0) {
+            if (t.is_right) out[(size_t)t.parent].right = me;
+            else            out[(size_t)t.parent].left = me;
+        }
+        if (t.hi - t.lo == 1) {
+            nd.leaf = items[t.lo].object;
+            out.push_back(nd);
+            continue;
+        }
+        out.push_back(nd);
+        double best_cost = INFINITY;
+        int best_axis = -1, best_bin = 0;
+        for (int a = 0; a < 3; ++a) {
+            const float extent = cmax[a] - cmin[a];
+            if (!(extent > 0.0f)) continue;
+            uint32_t cnt[kBins] = {0};
+            float bmn[kBins][3], bmx[kBins][3];
+            for (int b = 0; b < kBins; ++b)
+                for (int k = 0; k < 3; ++k) {
+                    bmn[b][k] = INFINITY;
+                    bmx[b][k] = -INFINITY;
+                }
+            const float scale = (float)kBins / extent;
+            for (uint32_t i = t.lo; i < t.hi; ++i) {
+                int b = (int)((items[i].c[a] - cmin[a]) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                ++cnt[b];
+                for (int k = 0; k < 3; ++k) {
+                    bmn[b][k] = std::fmin(bmn[b][k], items[i].bmin[k]);
+                    bmx[b][k] = std::fmax(bmx[b][k], items[i].bmax[k]);
+                }
+            }
+            double right_area[kBins];
+            uint32_t right_cnt[kBins];
+            float rmn[3] = {INFINITY, INFINITY, INFINITY}, rmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            uint32_t rc = 0;
+            for (int b = kBins - 1; b > 0; --b) {
+                for (int k = 0; k < 3; ++k) {
+                    rmn[k] = std::fmin(rmn[k], bmn[b][k]);
+                    rmx[k] = std::fmax(rmx[k], bmx[b][k]);
+                }
+                rc += cnt[b];
+                right_cnt[b] = rc;
+                right_area[b] = rc ? area(rmn, rmx) : 0.0;
+            }
+            float lmn[3] = {INFINITY, INFINITY, INFINITY}, lmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            uint32_t lc = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                for (int k = 0; k < 3; ++k) {
+                    lmn[k] = std::fmin(lmn[k], bmn[b][k]);
+                    lmx[k] = std::fmax(lmx[k], bmx[b][k]);
+                }
+                lc += cnt[b];
+                if (lc == 0 || right_cnt[b + 1] == 0) continue;
+                const double cost = area(lmn, lmx) * lc + right_area[b + 1] * right_cnt[b + 1];
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best_axis = a;
+                    best_bin = b;
+                }
+            }
+        }
+        uint32_t mid = t.lo + (t.hi - t.lo) / 2;
+        if (best_axis >= 0) {
+            const float scale = (float)kBins / (cmax[best_axis] - cmin[best_axis]);
+            const float c0 = cmin[best_axis];
+            const int a = best_axis, split = best_bin;
+            auto* first = items.data() + t.lo;
+            auto* last = items.data() + t.hi;
+            auto* m = std::partition(first, last, [=](const Item& it) {
+                int b = (int)((it.c[a] - c0) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                return b <= split;
+            });
+            const uint32_t pm = (uint32_t)(m - items.data());
+            if (pm > t.lo && pm < t.hi) mid = pm;
+        }
+        stack.push_back({mid, t.hi, me, true});
+        stack.push_back({t.lo, mid, me, false});
+    }
+    return 0;
+}
+
 static void scene_free(RtbScene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
@@ -314,11 +456,26 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     std::vector<float4> nodes(2 * (size_t)n_tree);
     emit_layout(desc, size, quad_slot, -1, false, nodes.data());
     // per-octant layouts, [mode][octant][2 * n_tree]
-    std::vector<float4> oct_nodes[2];
+    std::vector<float4> oct_nodes[3];
     for (int mode = 0; mode < 2; ++mode) {
         oct_nodes[mode].resize(16 * (size_t)n_tree);
         for (int oct = 0; oct < 8; ++oct)
             emit_layout(desc, size, quad_slot, oct, mode == 1, oct_nodes[mode].data() + (size_t)oct * 2 * n_tree);
+    }
+    {  // mode 2: the library's own SAH partition of the objects the host's tree references
+        std::vector<RtbBvhNode> sah_nodes;
+        RtbSceneDesc sah = *desc;
+        sah.root = build_sah(desc, size, sah_nodes);
+        sah.nodes = sah_nodes.data();
+        sah.n_nodes = (uint32_t)sah_nodes.size();
+        std::vector<uint32_t> sah_size;
+        uint32_t sah_depth = 0;
+        rc = tree_sizes(&sah, sah_size, &sah_depth);
+        if (rc != RTB_OK) return rc;
+        if (sah.n_nodes != n_tree) return fail(RTB_ERR_INVALID_ARGUMENT, "internal: SAH tree has %u nodes, expected %u", sah.n_nodes, n_tree);
+        oct_nodes[2].resize(16 * (size_t)n_tree);
+        for (int oct = 0; oct < 8; ++oct)
+            emit_layout(&sah, sah_size, quad_slot, oct, true, oct_nodes[2].data() + (size_t)oct * 2 * n_tree);
     }
     std::vector<float4> prims(2 * (size_t)desc->n_hittables);
     for (uint32_t i = 0; i < desc->n_hittables; ++i) leaf_record(desc, i, quad_slot, &prims[2 * (size_t)i], &prims[2 * (size_t)i + 1]);
@@ -378,6 +535,7 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     if (rc == RTB_OK) rc = upload(sc, nodes, &sc->dev.nodes);
     if (rc == RTB_OK) rc = upload(sc, oct_nodes[0], &sc->dev.oct_nodes[0]);
     if (rc == RTB_OK) rc = upload(sc, oct_nodes[1], &sc->dev.oct_nodes[1]);
+    if (rc == RTB_OK) rc = upload(sc, oct_nodes[2], &sc->dev.oct_nodes[2]);
     if (rc == RTB_OK) rc = upload(sc, prims, &sc->dev.prims);
     if (rc == RTB_OK) rc = upload(sc, obj_mat, &sc->dev.object_material);
     if (rc == RTB_OK) rc = upload(sc, mats, &sc->dev.materials);
@@ -417,7 +575,7 @@ extern "C" int rtb_scene_destroy(RtbScene* scene) {
 extern "C" int rtb_trace_rays(RtbScene* scene, const RtbRay* rays, uint64_t n, uint32_t traversal, RtbHit* hits_out) {
     if (!scene) return fail(RTB_ERR_INVALID_ARGUMENT, "scene is NULL");
     if (n && (!rays || !hits_out)) return fail(RTB_ERR_INVALID_ARGUMENT, "rays/hits_out is NULL");
-    if (traversal > RTB_TRAVERSAL_ORDERED) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", traversal);
+    if (traversal > RTB_TRAVERSAL_SAH) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", traversal);
     if (n == 0) return RTB_OK;
     std::lock_guard<std::mutex> lock(scene->mutex);
     RTB_CUDA(cudaSetDevice(scene->device));
@@ -426,7 +584,7 @@ extern "C" int rtb_trace_rays(RtbScene* scene, const RtbRay* rays, uint64_t n, u
     RTB_CUDA(cudaMalloc(&d_rays, n * sizeof(RtbRay)));
     cudaError_t e = cudaMalloc(&d_hits, n * sizeof(RtbHit));
     if (e == cudaSuccess) e = cudaMemcpy(d_rays, rays, n * sizeof(RtbRay), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_trace(scene->dev, d_rays, n, d_hits, traversal == RTB_TRAVERSAL_ORDERED, 0);
+    if (e == cudaSuccess) e = launch_trace(scene->dev, d_rays, n, d_hits, traversal, 0);
     if (e == cudaSuccess) e = cudaMemcpy(hits_out, d_hits, n * sizeof(RtbHit), cudaMemcpyDeviceToHost);
     cudaFree(d_rays);
     cudaFree(d_hits);
@@ -461,7 +619,7 @@ static int check_render_args(RtbScene* scene, const RtbCamera* cam, const RtbRen
     if (opt->tile_world > 0 && opt->tile_rank >= opt->tile_world) return fail(RTB_ERR_INVALID_ARGUMENT, "tile_rank >= tile_world");
     if (opt->integrator != RTB_INTEGRATOR_MEGAKERNEL && opt->integrator != RTB_INTEGRATOR_WAVEFRONT)
         return fail(RTB_ERR_INVALID_ARGUMENT, "unknown integrator %u", opt->integrator);
-    if (opt->traversal > RTB_TRAVERSAL_ORDERED) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", opt->traversal);
+    if (opt->traversal > RTB_TRAVERSAL_SAH) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", opt->traversal);
     if (cam->background_mode > RTB_BACKGROUND_SKY) return fail(RTB_ERR_INVALID_ARGUMENT, "unknown background mode");
     return RTB_OK;
 }
@@ -481,7 +639,7 @@ static int render_enqueue(RtbScene* scene, const RtbCamera* cam, const RtbRender
     p.pixel_end = (opt->pixel_begin == 0 && opt->pixel_count == 0) ? size : opt->pixel_begin + opt->pixel_count;
     p.tile_rank = opt->tile_rank;
     p.tile_world = opt->tile_world ? opt->tile_world : 1u;
-    p.ordered = opt->traversal == RTB_TRAVERSAL_ORDERED ? 1u : 0u;
+    p.ordered = opt->traversal;
     const bool count_work = (opt->flags & RTB_FLAG_COUNT_WORK) != 0;
     p.counters = count_work ? scene->d_counters : nullptr;
     if (opt->integrator == RTB_INTEGRATOR_WAVEFRONT) {

@@ -56,8 +56,9 @@ struct DevQuad {  // Quad fields incl. the ones Quad.init derives (src/objects.z
 struct DevScene {
     const float4* nodes;  // 2 per node: reference order, bounds as (min, max)
     // Per-octant layouts for the wavefront integrator, [mode][octant][2 * n_nodes], bounds pre-swapped
-    // to (entry plane, exit plane) for the octant.  mode 0 = reference order, 1 = near-child-first.
-    const float4* oct_nodes[2];
+    // to (entry plane, exit plane) for the octant.  mode 0 = reference order, 1 = near-child-first,
+    // 2 = the same objects re-partitioned by the library with a binned-SAH tree, near-child-first.
+    const float4* oct_nodes[3];
     const float4* prims;  // 2 per object: the leaf record {center1, kind|object}, {center_vec, radius}
     uint32_t n_nodes;
     uint32_t n_objects;

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderPar
                 Nearest best;
                 if (ORDERED) {
                     const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
-                    const float4* oct = P.scene.oct_nodes[1] + (size_t)ray_octant(ix, iy, iz) * 2u * P.scene.n_nodes;
+                    const float4* oct = P.scene.oct_nodes[P.ordered] + (size_t)ray_octant(ix, iy, iz) * 2u * P.scene.n_nodes;
                     best = traverse_octant<COUNT, QUADS>(oct, P.scene.n_nodes, P.scene.quads, ray.o, ray.d, ray.time, ix,
                                                          iy, iz, 0.001f, __int_as_float(0x7f800000), n_box, n_obj);
                 } else {
@@ -159,7 +159,7 @@ cudaError_t launch_megakernel(const RenderParams& p, bool nodes_in_smem, bool co
 // ------------------------------------------------------------------------------------------
 template <bool QUADS, bool ORDERED>
 __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const RtbRay* __restrict__ rays, uint64_t n,
-                                                    RtbHit* __restrict__ hits) {
+                                                    RtbHit* __restrict__ hits, uint32_t layout) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const RtbRay rr = rays[i];
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     Nearest best;
     if (ORDERED) {
         const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
-        const float4* oct = scene.oct_nodes[1] + (size_t)ray_octant(ix, iy, iz) * 2u * scene.n_nodes;
+        const float4* oct = scene.oct_nodes[layout] + (size_t)ray_octant(ix, iy, iz) * 2u * scene.n_nodes;
         best = traverse_octant<true, QUADS>(oct, scene.n_nodes, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min,
                                             rr.t_max, n_box, n_obj);
     } else {
@@ -200,16 +200,16 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     hits[i] = h;
 }
 
-cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n, RtbHit* d_hits, bool ordered,
+cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n, RtbHit* d_hits, uint32_t layout,
                          cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const uint32_t grid = (uint32_t)((n + 255u) / 256u);
     if (scene.has_quads) {
-        if (ordered) trace_kernel<true, true><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
-        else         trace_kernel<true, false><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
+        if (layout) trace_kernel<true, true><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits, layout);
+        else        trace_kernel<true, false><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits, 0u);
     } else {
-        if (ordered) trace_kernel<false, true><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
-        else         trace_kernel<false, false><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits);
+        if (layout) trace_kernel<false, true><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits, layout);
+        else        trace_kernel<false, false><<<grid, 256, 0, stream>>>(scene, d_rays, n, d_hits, 0u);
     }
     return cudaGetLastError();
 }

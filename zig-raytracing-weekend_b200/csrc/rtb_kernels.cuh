@@ -18,7 +18,7 @@ struct RenderParams {
     uint32_t sample_begin, sample_count;
     uint32_t pixel_begin, pixel_end;  // flat pixel range [begin, end)
     uint32_t tile_rank, tile_world;
-    uint32_t ordered;  // 0 = RTB_TRAVERSAL_REFERENCE, 1 = RTB_TRAVERSAL_ORDERED
+    uint32_t ordered;  // layout index = RTB_TRAVERSAL_* (0 reference order, 1 ordered, 2 SAH re-partition)
     unsigned long long* counters;  // [rays, box tests, object tests, hits] or nullptr
 };
 
@@ -32,7 +32,7 @@ cudaError_t launch_megakernel(const RenderParams& p, bool nodes_in_smem, bool co
                               LaunchInfo* info);
 
 // K3: nearest-hit query for a batch of rays (parity harness).
-cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n, RtbHit* d_hits, bool ordered,
+cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n, RtbHit* d_hits, uint32_t layout,
                          cudaStream_t stream);
 
 // K4: resolve (toGamma2 + truncation).

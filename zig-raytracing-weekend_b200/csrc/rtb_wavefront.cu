@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) wf_extend(const WfParams P) {
     if (blockIdx.x == 0 && threadIdx.x < kOctants) P.count_out[threadIdx.x] = 0u;
     __syncthreads();
     const uint32_t total_chunks = s_first_chunk[kOctants];
-    const float4* __restrict__ layouts = P.R.scene.oct_nodes[P.R.ordered ? 1 : 0];
+    const float4* __restrict__ layouts = P.R.scene.oct_nodes[P.R.ordered];
     uint32_t staged = kOctants;  // octant whose layout is in shared memory
     uint32_t n_box = 0, n_obj = 0, n_rays = 0;
     for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
