@@ -41,8 +41,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--integrator", default="auto", choices=["auto", "megakernel", "wavefront"])
-    ap.add_argument("--traversal", default="reference", choices=["reference", "ordered"],
-                    help="reference = the reference's left-then-right order (bit-exact hit index); ordered = near child first")
+    ap.add_argument("--traversal", default="sah", choices=["reference", "ordered", "sah"],
+                    help="reference = the reference's left-then-right order over the host's tree (bit-exact hit index); "
+                         "ordered = same tree, near child first; sah = the library's SAH re-partition of the same objects")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--depth", type=int, default=DEPTH)
@@ -207,7 +208,8 @@ def run_ours(a):
     d_rgba = torch.zeros(npx, 4, device=dev, dtype=torch.uint8)
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 
-    traversal = p.RTB_TRAVERSAL_ORDERED if a.traversal == "ordered" else p.RTB_TRAVERSAL_REFERENCE
+    traversal = {"reference": p.RTB_TRAVERSAL_REFERENCE, "ordered": p.RTB_TRAVERSAL_ORDERED,
+                 "sah": p.RTB_TRAVERSAL_SAH}[a.traversal]
 
     def make_options(step, integrator, flags=0, spp=None, trav=None):
         part = mg.plan(a.partition, rank, world_size, spp or a.spp, sample_base=0,
@@ -253,11 +255,17 @@ def run_ours(a):
     integ_name = "wavefront" if integrator == p.RTB_INTEGRATOR_WAVEFRONT else "megakernel"
 
     # -- algorithmic work per path (counting build, untimed, reduced spp: the ratios are spp-independent) -------
+    # `cst` = counters of the REFERENCE traversal (the algorithmic work of the task, SURVEY §8d: "a smarter traversal
+    # that visits fewer nodes still gets credit for the reference's counts ... report both"); `cst_act` = counters of
+    # the traversal actually timed.
     count_spp = max(1, min(a.spp, 16))
-    cst = step_device(0, integrator, count=True, spp=count_spp)
+    cst = step_device(0, integrator, count=True, spp=count_spp, trav=p.RTB_TRAVERSAL_REFERENCE)
+    cst_act = step_device(0, integrator, count=True, spp=count_spp)
     flops, bytes_ = algorithmic_work(cst, W, H)
     flops_per_path = flops / cst["n_paths"]
     bytes_per_path = (bytes_ - 20 * npx) / cst["n_paths"]
+    flops_act, _ = algorithmic_work(cst_act, W, H)
+    flops_act_per_path = flops_act / cst_act["n_paths"]
 
     # -- warm-up ----------------------------------------------------------------------------------------------
     for w in range(a.warmup):
@@ -309,8 +317,10 @@ def run_ours(a):
     variants = {}
     for vname, vint, vtrav in (("megakernel/reference", p.RTB_INTEGRATOR_MEGAKERNEL, p.RTB_TRAVERSAL_REFERENCE),
                                ("megakernel/ordered", p.RTB_INTEGRATOR_MEGAKERNEL, p.RTB_TRAVERSAL_ORDERED),
+                               ("megakernel/sah", p.RTB_INTEGRATOR_MEGAKERNEL, p.RTB_TRAVERSAL_SAH),
                                ("wavefront/reference", p.RTB_INTEGRATOR_WAVEFRONT, p.RTB_TRAVERSAL_REFERENCE),
-                               ("wavefront/ordered", p.RTB_INTEGRATOR_WAVEFRONT, p.RTB_TRAVERSAL_ORDERED)):
+                               ("wavefront/ordered", p.RTB_INTEGRATOR_WAVEFRONT, p.RTB_TRAVERSAL_ORDERED),
+                               ("wavefront/sah", p.RTB_INTEGRATOR_WAVEFRONT, p.RTB_TRAVERSAL_SAH)):
         vspp = max(1, min(a.spp, 100))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -380,6 +390,15 @@ def run_ours(a):
         "peak_source": "FFMA microbenchmark measured in this run (FMA = 2 flops); the kernels run unfused, ceiling = peak/2",
         "traffic": None,
         "algorithmic_flops_per_path": flops_per_path, "kernel_ms_per_step": kernel_ms,
+        "counting": "achieved = flops of the REFERENCE traversal (left-then-right over the host's tree, SURVEY 8d) "
+                    "/ kernel time; achieved_actual = flops of the traversal that ran",
+        "achieved_actual": flops_act_per_path * paths_per_launch_group / (kernel_ms * 1e-3) / 1e12,
+        "frac_actual": flops_act_per_path * paths_per_launch_group / (kernel_ms * 1e-3) / 1e12 / fp32_peak,
+        "actual_flops_per_path": flops_act_per_path,
+        "actual_work_per_path": {"rays": cst_act["n_rays"] / cst_act["n_paths"],
+                                 "box_tests": cst_act["n_box_tests"] / cst_act["n_paths"],
+                                 "object_tests": cst_act["n_object_tests"] / cst_act["n_paths"],
+                                 "hits": cst_act["n_hits"] / cst_act["n_paths"]},
         "hbm": {"achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved_gbs / peaks["hbm_gbs"], "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                 "algorithmic_bytes_per_path": bytes_per_path},

@@ -455,12 +455,14 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     const uint32_t n_tree = desc->n_nodes ? size[desc->root] : 0u;
     std::vector<float4> nodes(2 * (size_t)n_tree);
     emit_layout(desc, size, quad_slot, -1, false, nodes.data());
-    // per-octant layouts, [mode][octant][2 * n_tree]
+    // per-octant layouts, [mode][octant][2 * (n_tree + 1)]; entry n_tree of every octant is the end sentinel
+    const size_t oct_stride = 2 * ((size_t)n_tree + 1);
+    const float4 sentinel = mkf4(0.0f, 0.0f, 0.0f, bits(RTB_META_END));
     std::vector<float4> oct_nodes[3];
     for (int mode = 0; mode < 2; ++mode) {
-        oct_nodes[mode].resize(16 * (size_t)n_tree);
+        oct_nodes[mode].assign(8 * oct_stride, sentinel);
         for (int oct = 0; oct < 8; ++oct)
-            emit_layout(desc, size, quad_slot, oct, mode == 1, oct_nodes[mode].data() + (size_t)oct * 2 * n_tree);
+            emit_layout(desc, size, quad_slot, oct, mode == 1, oct_nodes[mode].data() + (size_t)oct * oct_stride);
     }
     {  // mode 2: the library's own SAH partition of the objects the host's tree references
         std::vector<RtbBvhNode> sah_nodes;
@@ -473,12 +475,10 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
         rc = tree_sizes(&sah, sah_size, &sah_depth);
         if (rc != RTB_OK) return rc;
         if (sah.n_nodes != n_tree) return fail(RTB_ERR_INVALID_ARGUMENT, "internal: SAH tree has %u nodes, expected %u", sah.n_nodes, n_tree);
-        oct_nodes[2].resize(16 * (size_t)n_tree);
+        oct_nodes[2].assign(8 * oct_stride, sentinel);
         for (int oct = 0; oct < 8; ++oct)
-            emit_layout(&sah, sah_size, quad_slot, oct, true, oct_nodes[2].data() + (size_t)oct * 2 * n_tree);
+            emit_layout(&sah, sah_size, quad_slot, oct, true, oct_nodes[2].data() + (size_t)oct * oct_stride);
     }
-    std::vector<float4> prims(2 * (size_t)desc->n_hittables);
-    for (uint32_t i = 0; i < desc->n_hittables; ++i) leaf_record(desc, i, quad_slot, &prims[2 * (size_t)i], &prims[2 * (size_t)i + 1]);
 
     RtbScene* sc = new (std::nothrow) RtbScene();
     if (!sc) return fail(RTB_ERR_OUT_OF_MEMORY, "host allocation failed");
@@ -501,6 +501,21 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
         }
         mats[2 * (size_t)i] = mkf4(bits(m.type | (tex_type << 8)), bits(has_tex ? m.texture : 0u), m.fuzz, m.ir);
         mats[2 * (size_t)i + 1] = mkf4(rgb[0], rgb[1], rgb[2], 0.0f);
+    }
+    // per-object record for the wavefront shader: leaf record + the object's material record, and its class
+    std::vector<float4> prims(4 * (size_t)desc->n_hittables);
+    std::vector<uint8_t> obj_class(desc->n_hittables);
+    for (uint32_t i = 0; i < desc->n_hittables; ++i) {
+        leaf_record(desc, i, quad_slot, &prims[4 * (size_t)i], &prims[4 * (size_t)i + 1]);
+        const uint32_t m = desc->hittables[i].material;
+        prims[4 * (size_t)i + 2] = mats[2 * (size_t)m];
+        prims[4 * (size_t)i + 3] = mats[2 * (size_t)m + 1];
+        const RtbMaterial& mat = desc->materials[m];
+        uint8_t cls = CLASS_OTHER;
+        if (mat.type == RTB_MAT_LAMBERTIAN && desc->textures[mat.texture].type == RTB_TEX_SOLID) cls = CLASS_LAMBERT_SOLID;
+        if (mat.type == RTB_MAT_METAL) cls = CLASS_METAL;
+        if (mat.type == RTB_MAT_DIELECTRIC) cls = CLASS_DIELECTRIC;
+        obj_class[i] = cls;
     }
     std::vector<float4> texs(3 * (size_t)desc->n_textures);
     for (uint32_t i = 0; i < desc->n_textures; ++i) {
@@ -537,6 +552,7 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     if (rc == RTB_OK) rc = upload(sc, oct_nodes[1], &sc->dev.oct_nodes[1]);
     if (rc == RTB_OK) rc = upload(sc, oct_nodes[2], &sc->dev.oct_nodes[2]);
     if (rc == RTB_OK) rc = upload(sc, prims, &sc->dev.prims);
+    if (rc == RTB_OK) rc = upload(sc, obj_class, &sc->dev.object_class);
     if (rc == RTB_OK) rc = upload(sc, obj_mat, &sc->dev.object_material);
     if (rc == RTB_OK) rc = upload(sc, mats, &sc->dev.materials);
     if (rc == RTB_OK) rc = upload(sc, texs, &sc->dev.textures);

@@ -30,6 +30,9 @@ namespace rtb {
 //             next = i + 1 (a leaf's successor in pre-order is the next node)
 //   quad    : f0 = {0,0,0, bits(KIND_QUAD<<30 | object)}        f1 = {0,0,0, bits(quad slot)}
 enum : uint32_t { KIND_INTERIOR = 0u, KIND_SPHERE = 1u, KIND_MOVING_SPHERE = 2u, KIND_QUAD = 3u };
+// Shading classes for hit binning in the wavefront integrator: rays that missed, and hits by material kind.
+enum : uint32_t { CLASS_MISS = 0u, CLASS_LAMBERT_SOLID = 1u, CLASS_METAL = 2u, CLASS_DIELECTRIC = 3u, CLASS_OTHER = 4u,
+                  kShadeClasses = 5u };
 #define RTB_META_INDEX_MASK 0x3fffffffu
 
 // Material record, 2 x float4:
@@ -58,8 +61,13 @@ struct DevScene {
     // Per-octant layouts for the wavefront integrator, [mode][octant][2 * n_nodes], bounds pre-swapped
     // to (entry plane, exit plane) for the octant.  mode 0 = reference order, 1 = near-child-first,
     // 2 = the same objects re-partitioned by the library with a binned-SAH tree, near-child-first.
+    // Each octant's array holds n_nodes + 1 entries: the last one is the end sentinel (RTB_META_END).
     const float4* oct_nodes[3];
-    const float4* prims;  // 2 per object: the leaf record {center1, kind|object}, {center_vec, radius}
+    // 4 per object: the leaf record {center1, kind|object}, {center_vec, radius} and the object's material
+    // record {m0, m1} inlined (the reference stores Material by value in every Hittable anyway).
+    const float4* prims;
+    // Shading class of each object (ShadeClass), used to bin hits so that a warp shades one material kind.
+    const uint8_t* object_class;
     uint32_t n_nodes;
     uint32_t n_objects;
     const uint32_t* object_material;  // object index -> material index
@@ -290,24 +298,46 @@ __device__ __forceinline__ bool sphere_root_a(float3 o, float3 d, float a, float
 // Traversal over one octant's threaded layout (DevScene::oct_nodes).  Visiting order is whatever the
 // host baked into the layout: the reference's left-then-right order (RTB_TRAVERSAL_REFERENCE) or
 // near-child-first for this octant (RTB_TRAVERSAL_ORDERED).  Nearest.node is the OBJECT index.
-template <bool COUNT, bool QUADS>
-__device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ nodes, uint32_t n_nodes,
-                                                   const DevQuad* __restrict__ quads, float3 o, float3 d, float time,
-                                                   float inv_x, float inv_y, float inv_z, float t_min, float t_max,
-                                                   uint32_t& n_box, uint32_t& n_obj) {
+// The per-octant layouts end with a SENTINEL node (meta = RTB_META_END) at index n_nodes, the target of
+// every skip link that leaves the tree, so the hot slab path carries no loop-bound test.  With SMEM the
+// node array is the kernel's dynamic shared memory (indexed directly, so the LDS address is base + i*32
+// without a generic-pointer conversion per iteration).
+#define RTB_META_END 0xffffffffu
+extern __shared__ float4 rtb_smem_nodes[];
+
+template <bool COUNT, bool QUADS, bool SMEM>
+__device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ nodes, const DevQuad* __restrict__ quads,
+                                                   float3 o, float3 d, float time, float inv_x, float inv_y,
+                                                   float inv_z, float t_min, float t_max, uint32_t& n_box,
+                                                   uint32_t& n_obj, uint32_t smem_base = 0u) {
+    // smem_base (SMEM only): 32-bit shared-window address of the staged layout.  The caller adds a
+    // run-time zero to it so that ptxas keeps it in a register instead of rematerialising the window
+    // base (S2UR/UMOV/UIADD3/ULEA) in every iteration of the node loop.
     Nearest best;
     best.t = t_max;
     best.node = 0xffffffffu;
     const float a = length_squared(d);
     uint32_t i = 0;
-    while (i < n_nodes) {
-        const float4 f0 = nodes[2u * i];
-        const float4 f1 = nodes[2u * i + 1u];
+    for (;;) {
+        float4 f0, f1;
+        if (SMEM) {
+            const uint32_t addr = smem_base + i * 32u;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(f0.x), "=f"(f0.y), "=f"(f0.z), "=f"(f0.w)
+                         : "r"(addr));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];"
+                         : "=f"(f1.x), "=f"(f1.y), "=f"(f1.z), "=f"(f1.w)
+                         : "r"(addr));
+        } else {
+            f0 = nodes[2u * i];
+            f1 = nodes[2u * i + 1u];
+        }
         const uint32_t meta = __float_as_uint(f0.w);
         if (meta < (1u << 30)) {  // KIND_INTERIOR: meta is the skip index
             if (COUNT) ++n_box;
             i = slab_miss_preswapped(f0, f1, o, inv_x, inv_y, inv_z, t_min, best.t) ? meta : i + 1u;
         } else {
+            if (meta == RTB_META_END) break;
             if (COUNT) ++n_obj;
             const uint32_t kind = meta >> 30;
             if (!QUADS || kind != KIND_QUAD) {
@@ -403,16 +433,14 @@ __device__ __forceinline__ void sphere_uv(float3 p, float& u, float& v) {
 // The part of Sphere.hit / Quad.hit after the root is accepted (src/objects.zig:139-147, :250-260),
 // evaluated once for the nearest hit instead of once per candidate.
 template <bool QUADS, bool WANT_UV>
-__device__ __forceinline__ DHit finish_hit(const float4* __restrict__ nodes, const DevQuad* __restrict__ quads,
-                                           const DRay& r, Nearest best) {
+__device__ __forceinline__ DHit finish_hit_rec(float4 f0, float4 f1, const DevQuad* __restrict__ quads, const DRay& r,
+                                               float t) {
     DHit h;
-    const float4 f0 = nodes[2u * best.node];
-    const float4 f1 = nodes[2u * best.node + 1u];
     const uint32_t meta = __float_as_uint(f0.w);
     const uint32_t kind = meta >> 30;
     h.object = meta & RTB_META_INDEX_MASK;
-    h.t = best.t;
-    h.p = r.o + splat3(best.t) * r.d;  // Ray.at, src/ray.zig:9-11
+    h.t = t;
+    h.p = r.o + splat3(t) * r.d;  // Ray.at, src/ray.zig:9-11
     h.u = 0.0f;
     h.v = 0.0f;
     float3 outward;
@@ -433,6 +461,13 @@ __device__ __forceinline__ DHit finish_hit(const float4* __restrict__ nodes, con
     h.front_face = dot3(r.d, outward) < 0.0f;  // setFaceNormal, src/objects.zig:30-36
     h.normal = h.front_face ? outward : -outward;
     return h;
+}
+
+// Same, with the leaf record fetched from a node / prim array (2 float4 per entry).
+template <bool QUADS, bool WANT_UV>
+__device__ __forceinline__ DHit finish_hit(const float4* __restrict__ nodes, const DevQuad* __restrict__ quads,
+                                           const DRay& r, Nearest best) {
+    return finish_hit_rec<QUADS, WANT_UV>(nodes[2u * best.node], nodes[2u * best.node + 1u], quads, r, best.t);
 }
 
 // ------------------------------------------------------------------ textures
@@ -535,24 +570,21 @@ struct ShadeResult {
 
 // emitted + scatter for the nearest hit (src/camera.zig:194-196 -> src/material.zig:18-30).
 // `segment` (>= 1) keys this hit's RNG stream; block 0 word 3 is the dielectric reflectance draw.
+// `f0,f1` = the hit object's leaf record, `m0,m1` = its material record.
 template <bool QUADS>
-__device__ __forceinline__ ShadeResult shade(const DevScene& sc, const float4* __restrict__ nodes, const DRay& r,
-                                             Nearest best, const RngKey& key, uint32_t segment) {
+__device__ __forceinline__ ShadeResult shade_rec(const DevScene& sc, float4 f0, float4 f1, float4 m0, float4 m1,
+                                                 const DRay& r, float t, const RngKey& key, uint32_t segment) {
     ShadeResult out;
     const TexTables tt{sc.textures, sc.perlins, sc.images};
     out.emitted = f3(0.0f, 0.0f, 0.0f);
-    const uint32_t object = __float_as_uint(nodes[2u * best.node].w) & RTB_META_INDEX_MASK;
-    const uint32_t mat = sc.object_material[object];
-    const float4 m0 = sc.materials[2u * mat];
-    const float4 m1 = sc.materials[2u * mat + 1u];
     const uint32_t tag = __float_as_uint(m0.x);
     const uint32_t type = tag & 0xffu;
     const uint32_t tex_type = (tag >> 8) & 0xffu;
     DHit h;
     if (texture_needs_uv(tex_type))
-        h = finish_hit<QUADS, true>(nodes, sc.quads, r, best);
+        h = finish_hit_rec<QUADS, true>(f0, f1, sc.quads, r, t);
     else
-        h = finish_hit<QUADS, false>(nodes, sc.quads, r, best);
+        h = finish_hit_rec<QUADS, false>(f0, f1, sc.quads, r, t);
     out.scattered.o = h.p;
     out.scattered.time = r.time;
     if (type == RTB_MAT_LAMBERTIAN) {  // src/material.zig:43-54
@@ -596,6 +628,16 @@ __device__ __forceinline__ ShadeResult shade(const DevScene& sc, const float4* _
         out.scatters = true;
     }
     return out;
+}
+
+// shade_rec with the records fetched through the node/prim array, object -> material table.
+template <bool QUADS>
+__device__ __forceinline__ ShadeResult shade(const DevScene& sc, const float4* __restrict__ nodes, const DRay& r,
+                                             Nearest best, const RngKey& key, uint32_t segment) {
+    const float4 f0 = nodes[2u * best.node];
+    const float4 f1 = nodes[2u * best.node + 1u];
+    const uint32_t mat = sc.object_material[__float_as_uint(f0.w) & RTB_META_INDEX_MASK];
+    return shade_rec<QUADS>(sc, f0, f1, sc.materials[2u * mat], sc.materials[2u * mat + 1u], r, best.t, key, segment);
 }
 
 // Miss colour: solid background (src/camera.zig:207) or the legacy sky gradient (:204-206).

@@ -21,14 +21,13 @@ namespace rtb {
 // memory); Nearest.node is then an object index and the leaf records come from scene.prims.
 template <bool SMEM_NODES, bool COUNT, bool QUADS, bool ORDERED>
 __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderParams P) {
-    extern __shared__ float4 s_nodes[];
+    float4* s_nodes = rtb_smem_nodes;
     const float4* __restrict__ nodes = P.scene.nodes;
     if (SMEM_NODES && !ORDERED) {
         for (uint32_t i = threadIdx.x; i < 2u * P.scene.n_nodes; i += kCtaThreads) s_nodes[i] = P.scene.nodes[i];
         __syncthreads();
         nodes = s_nodes;
     }
-    const float4* __restrict__ leaves = ORDERED ? P.scene.prims : nodes;
 
     const uint32_t tiles_x = (P.cam.width + kTileW - 1u) / kTileW;
     const uint32_t tile = blockIdx.x * P.tile_world + P.tile_rank;
@@ -56,9 +55,10 @@ __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderPar
                 Nearest best;
                 if (ORDERED) {
                     const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
-                    const float4* oct = P.scene.oct_nodes[P.ordered] + (size_t)ray_octant(ix, iy, iz) * 2u * P.scene.n_nodes;
-                    best = traverse_octant<COUNT, QUADS>(oct, P.scene.n_nodes, P.scene.quads, ray.o, ray.d, ray.time, ix,
-                                                         iy, iz, 0.001f, __int_as_float(0x7f800000), n_box, n_obj);
+                    const float4* oct =
+                        P.scene.oct_nodes[P.ordered] + (size_t)ray_octant(ix, iy, iz) * 2u * (P.scene.n_nodes + 1u);
+                    best = traverse_octant<COUNT, QUADS, false>(oct, P.scene.quads, ray.o, ray.d, ray.time, ix, iy, iz,
+                                                                0.001f, __int_as_float(0x7f800000), n_box, n_obj);
                 } else {
                     best = traverse_reference<COUNT, QUADS>(nodes, P.scene.n_nodes, P.scene.quads, ray, 0.001f,
                                                             __int_as_float(0x7f800000), n_box, n_obj);
@@ -69,7 +69,13 @@ __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderPar
                     done = true;
                 } else {
                     if (COUNT) ++n_hits;
-                    const ShadeResult sr = shade<QUADS>(P.scene, leaves, ray, best, key, segment);
+                    ShadeResult sr;
+                    if (ORDERED) {
+                        const float4* pr = P.scene.prims + 4u * (size_t)best.node;
+                        sr = shade_rec<QUADS>(P.scene, pr[0], pr[1], pr[2], pr[3], ray, best.t, key, segment);
+                    } else {
+                        sr = shade<QUADS>(P.scene, nodes, ray, best, key, segment);
+                    }
                     L = L + T * sr.emitted;
                     if (sr.scatters && segment < P.cam.max_depth) {
                         T = T * sr.attenuation;
@@ -171,9 +177,9 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     Nearest best;
     if (ORDERED) {
         const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
-        const float4* oct = scene.oct_nodes[layout] + (size_t)ray_octant(ix, iy, iz) * 2u * scene.n_nodes;
-        best = traverse_octant<true, QUADS>(oct, scene.n_nodes, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min,
-                                            rr.t_max, n_box, n_obj);
+        const float4* oct = scene.oct_nodes[layout] + (size_t)ray_octant(ix, iy, iz) * 2u * (scene.n_nodes + 1u);
+        best = traverse_octant<true, QUADS, false>(oct, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min, rr.t_max,
+                                                   n_box, n_obj);
     } else {
         best = traverse_reference<true, QUADS>(scene.nodes, scene.n_nodes, scene.quads, r, rr.t_min, rr.t_max, n_box,
                                                n_obj);
@@ -186,7 +192,9 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     h.normal[0] = h.normal[1] = h.normal[2] = 0.0f;
     h.u = h.v = 0.0f;
     if (best.node != 0xffffffffu) {
-        const DHit d = finish_hit<QUADS, true>(ORDERED ? scene.prims : scene.nodes, scene.quads, r, best);
+        const DHit d = ORDERED ? finish_hit_rec<QUADS, true>(scene.prims[4u * (size_t)best.node],
+                                                             scene.prims[4u * (size_t)best.node + 1u], scene.quads, r, best.t)
+                               : finish_hit<QUADS, true>(scene.nodes, scene.quads, r, best);
         h.object = (int32_t)d.object;
         h.front_face = d.front_face ? 1u : 0u;
         h.t = d.t;

@@ -1,8 +1,7 @@
 // rtb_wavefront.cu — K2: wavefront integrator, sm_100a, compiled -fmad=false.
 //
 // The same per-path arithmetic as the megakernel (rtb_device.cuh), split by stage, with the live rays
-// kept in compacted SoA queues in HBM, BINNED BY RAY OCTANT (the three `invD < 0` predicates of
-// Aabb.hit, src/aabb.zig:97):
+// kept in compacted SoA queues in HBM:
 //   wf_raygen      Camera.getRay for (pixel, sample) slots                (src/camera.zig:169-180)
 //   wf_extend      world.hit for every queued ray                          (src/bvh.zig:122-136)
 //   wf_shade       emitted + scatter; surviving rays go to the next bounce's queues
@@ -12,14 +11,18 @@
 // the RNG stream key — is a kernel argument and only the slot id travels with a ray; throughput and
 // gathered radiance stay in per-slot arrays.
 //
-// Why octant bins (evidence: profiles/r1a_*, r1b_*): ncu showed the extend kernel issue-bound on the
-// half-rate ALU pipe (FSEL/FSETP/FMNMX), not on memory.  A CTA that only sees rays of one octant can
-// stage THAT octant's node layout in shared memory, in which every slab is already stored as (entry
-// plane, exit plane): the reference's per-visit swap `if (invD < 0)` (6 FSEL + 3 FSETP) disappears,
-// and the layout may also bake in near-child-first order (RTB_TRAVERSAL_ORDERED) while staying a
-// stackless skip-link walk.  Three persistent variants of the kernel (per-lane refill from the queue,
-// with and without leaf batching / while-while) were measured on B200 and all lost to this plain
-// one-thread-per-ray loop, so they are not kept.
+// Two levels of binning keep warps coherent (evidence: profiles/r1a_*, r1c_*, r1d_*):
+//   * RAY queues are binned by ray OCTANT (the three `invD < 0` predicates of Aabb.hit,
+//     src/aabb.zig:97).  A CTA that only sees rays of one octant stages THAT octant's node layout in
+//     shared memory, in which every slab is already stored as (entry plane, exit plane): the
+//     reference's per-visit swap (6 FSEL + 3 FSETP on the half-rate ALU pipe) disappears, and the
+//     layout may bake in near-child-first order while staying a stackless skip-link walk.
+//   * HIT queues are binned by SHADING CLASS (miss / lambertian / metal / dielectric / other): ncu
+//     showed the shade kernel executing every material's code in every warp (890 warp-instructions per
+//     warp, 11-18 of 32 lanes active); with one class per 256-ray chunk a warp runs one material path.
+// Three persistent variants of the extend kernel (per-lane refill from the queue, with and without
+// leaf batching / while-while) were measured on B200 and all lost to the plain one-thread-per-ray
+// loop, so they are not kept.
 #include "rtb_wavefront.cuh"
 
 #include <new>
@@ -27,21 +30,23 @@
 namespace rtb {
 
 constexpr uint32_t kOctants = 8;
+constexpr uint32_t kBins = 8;     // counters per binned queue set (8 octants; 5 shading classes, padded)
 constexpr uint32_t kChunk = 256;  // rays per CTA pass
 
+// 32-byte records everywhere (= one DRAM sector), because the shade kernel GATHERS them: ncu (r1e) showed
+// it DRAM-bound at ~50 % of HBM peak fetching 16 B pieces out of separate arrays, two sectors per 32 B used.
 struct WfQueue {
-    float4* o_time;  // [octant][capacity] origin.xyz, time
-    float4* d_slot;  // [octant][capacity] direction.xyz, bits(slot)
+    float4* rays;  // [octant][capacity][2]: {origin.xyz, time}, {direction.xyz, bits(slot)}
 };
 
 // One pipeline lane: the queues of one in-flight batch and the stream its kernels run on.
 struct WfLane {
     size_t capacity = 0;  // slots
     WfQueue q[2]{};
-    float2* hits = nullptr;      // [octant][capacity] t, bits(object)
-    float4* T = nullptr;         // [capacity] throughput
-    float4* L = nullptr;         // [capacity] radiance gathered so far; final radiance once the path ends
-    uint32_t* counts = nullptr;  // [2][8] queue sizes
+    uint4* hitq = nullptr;       // [class][capacity] {ray position, bits(t), object, -}
+    float4* TL = nullptr;        // [capacity][2]: {T.xyz, L.x}, {L.y, L.z, -, -}: throughput and radiance so far
+                                 // (the final radiance once the path has ended)
+    uint32_t* counts = nullptr;  // [2][8] ray-queue sizes, then [2][8] hit-queue sizes
     cudaStream_t stream = nullptr;
     cudaEvent_t accumulated = nullptr;  // recorded after this lane's wf_accumulate
 };
@@ -58,16 +63,18 @@ struct WavefrontState {
 struct WfParams {
     RenderParams R;
     WfQueue in, out;
-    float2* hits;
-    float4* T;
-    float4* L;
-    const uint32_t* count_in;  // 8
-    uint32_t* count_out;       // 8
-    uint32_t capacity;          // stride between octant bins
+    uint4* hitq;
+    float4* TL;
+    const uint32_t* count_in;   // 8: ray bins of this bounce
+    uint32_t* count_out;        // 8: ray bins of the next bounce
+    uint32_t* hit_count;        // 8: hit bins of this bounce
+    uint32_t* hit_count_next;   // 8: hit bins of the next bounce (cleared by this bounce's extend)
+    uint32_t capacity;          // stride between bins
     uint32_t slots_per_sample;  // owned tiles * 256
     uint32_t batch_begin;       // first sample of this batch
     uint32_t batch_samples;     // samples in flight per pixel in this batch
     uint32_t segment;           // 1-based segment index of the rays in `in`
+    uint32_t zero;              // always 0; only there to make an address opaque to ptxas (see traverse_octant)
 };
 
 __device__ __forceinline__ bool slot_pixel(const RenderParams& R, uint32_t r, uint32_t& pixel) {
@@ -81,14 +88,14 @@ __device__ __forceinline__ bool slot_pixel(const RenderParams& R, uint32_t r, ui
     return px < R.cam.width && py < R.cam.height && pixel >= R.pixel_begin && pixel < R.pixel_end;
 }
 
-// Warp-aggregated push into one of 8 bins: one atomicAdd per (warp, octant present in the warp).
+// Warp-aggregated push into one of up to 8 bins: one atomicAdd per (warp, bin present in the warp).
 // Must be called by all 32 lanes.
-__device__ __forceinline__ uint32_t queue_reserve(uint32_t* counts8, bool push, uint32_t octant) {
+__device__ __forceinline__ uint32_t queue_reserve(uint32_t* counts8, bool push, uint32_t bin) {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, push ? octant : kOctants);
+    const uint32_t peers = __match_any_sync(0xffffffffu, push ? bin : kBins);
     const uint32_t leader = __ffs(peers) - 1u;
     uint32_t base = 0;
-    if (push && lane == leader) base = atomicAdd(&counts8[octant], __popc(peers));
+    if (push && lane == leader) base = atomicAdd(&counts8[bin], __popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
     return base + __popc(peers & ((1u << lane) - 1u));
 }
@@ -103,9 +110,28 @@ __device__ __forceinline__ void push_ray(const WfParams& P, const DRay& ray, uin
     const uint32_t j = queue_reserve(P.count_out, push, oct);
     if (push) {
         const size_t at = (size_t)oct * P.capacity + j;
-        P.out.o_time[at] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.time);
-        P.out.d_slot[at] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(slot));
+        P.out.rays[2u * at] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.time);
+        P.out.rays[2u * at + 1u] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(slot));
     }
+}
+
+// Splits the concatenation of `n_bins` queues into 256-entry chunks; chunk c of a CTA's walk
+// (c = blockIdx.x, += gridDim.x) lies in exactly one bin, and the bins it meets are non-decreasing.
+struct ChunkMap {
+    uint32_t count[kBins];
+    uint32_t first_chunk[kBins + 1];
+};
+__device__ __forceinline__ void chunk_map_init(ChunkMap& m, const uint32_t* counts, uint32_t n_bins) {
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (uint32_t b = 0; b < kBins; ++b) {
+            m.count[b] = b < n_bins ? counts[b] : 0u;
+            m.first_chunk[b] = acc;
+            acc += (m.count[b] + kChunk - 1u) / kChunk;
+        }
+        m.first_chunk[kBins] = acc;
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
@@ -120,14 +146,14 @@ __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
         if (slot < total) {
             uint32_t pixel;
             if (slot_pixel(P.R, slot % P.slots_per_sample, pixel)) {
-                P.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                P.TL[2u * (size_t)slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+                P.TL[2u * (size_t)slot + 1u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (P.R.cam.max_depth != 0u) {
                     RngKey key;
                     key.seed = P.R.seed;
                     key.pixel = pixel;
                     key.sample = P.batch_begin + slot / P.slots_per_sample;
                     ray = get_ray(P.R.cam, key);
-                    P.T[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
                     push = true;
                 }
             }
@@ -136,54 +162,53 @@ __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
     }
 }
 
-// One thread per ray, plain node loop.  A CTA walks 256-ray chunks of the concatenated bins; chunks
-// it visits are in non-decreasing octant order, so it re-stages the node layout at most 8 times.
+// One thread per ray, plain node loop over the octant's layout; the result goes to the hit queue of
+// the hit object's shading class.
 template <bool SMEM_NODES, bool COUNT, bool QUADS>
 __global__ void __launch_bounds__(256) wf_extend(const WfParams P) {
-    extern __shared__ float4 s_nodes[];
-    __shared__ uint32_t s_count[kOctants], s_first_chunk[kOctants + 1];
+    __shared__ ChunkMap map;
     const uint32_t n_nodes = P.R.scene.n_nodes;
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (uint32_t o = 0; o < kOctants; ++o) {
-            s_count[o] = P.count_in[o];
-            s_first_chunk[o] = acc;
-            acc += (s_count[o] + kChunk - 1u) / kChunk;
-        }
-        s_first_chunk[kOctants] = acc;
+    chunk_map_init(map, P.count_in, kOctants);
+    // Bins nobody reads during this kernel: the ray bins this bounce's shade kernel will push into and
+    // the hit bins of the next bounce.
+    if (blockIdx.x == 0 && threadIdx.x < kBins) {
+        P.count_out[threadIdx.x] = 0u;
+        P.hit_count_next[threadIdx.x] = 0u;
     }
-    // The bins this bounce's shade kernel will push into are not read by anyone now: clear them here.
-    if (blockIdx.x == 0 && threadIdx.x < kOctants) P.count_out[threadIdx.x] = 0u;
-    __syncthreads();
-    const uint32_t total_chunks = s_first_chunk[kOctants];
+    const uint32_t total_chunks = map.first_chunk[kBins];
+    const size_t oct_stride = 2u * ((size_t)n_nodes + 1u);
     const float4* __restrict__ layouts = P.R.scene.oct_nodes[P.R.ordered];
     uint32_t staged = kOctants;  // octant whose layout is in shared memory
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(rtb_smem_nodes) + P.zero;
     uint32_t n_box = 0, n_obj = 0, n_rays = 0;
     for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
         uint32_t oct = 0;
-        while (c >= s_first_chunk[oct + 1u]) ++oct;
-        const float4* __restrict__ nodes = layouts + (size_t)oct * 2u * n_nodes;
-        if (SMEM_NODES) {
-            if (oct != staged) {
-                __syncthreads();
-                for (uint32_t i = threadIdx.x; i < 2u * n_nodes; i += blockDim.x) s_nodes[i] = nodes[i];
-                __syncthreads();
-                staged = oct;
-            }
-            nodes = s_nodes;
+        while (c >= map.first_chunk[oct + 1u]) ++oct;
+        const float4* __restrict__ nodes = layouts + (size_t)oct * oct_stride;
+        if (SMEM_NODES && oct != staged) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < (uint32_t)oct_stride; i += blockDim.x) rtb_smem_nodes[i] = nodes[i];
+            __syncthreads();
+            staged = oct;
         }
-        const uint32_t i = (c - s_first_chunk[oct]) * kChunk + threadIdx.x;
-        if (i < s_count[oct]) {
+        const uint32_t i = (c - map.first_chunk[oct]) * kChunk + threadIdx.x;
+        const bool valid = i < map.count[oct];
+        uint32_t cls = CLASS_MISS;
+        uint4 entry = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
             const size_t at = (size_t)oct * P.capacity + i;
-            const float4 a = P.in.o_time[at];
-            const float4 b = P.in.d_slot[at];
+            const float4 a = P.in.rays[2u * at];
+            const float4 b = P.in.rays[2u * at + 1u];
             const float3 o = f3(a), d = f3(b);
             if (COUNT) ++n_rays;
-            const Nearest best = traverse_octant<COUNT, QUADS>(nodes, n_nodes, P.R.scene.quads, o, d, a.w, 1.0f / d.x,
-                                                               1.0f / d.y, 1.0f / d.z, 0.001f,
-                                                               __int_as_float(0x7f800000), n_box, n_obj);
-            P.hits[at] = make_float2(best.t, __uint_as_float(best.node));
+            const Nearest best = traverse_octant<COUNT, QUADS, SMEM_NODES>(
+                nodes, P.R.scene.quads, o, d, a.w, 1.0f / d.x, 1.0f / d.y, 1.0f / d.z, 0.001f, __int_as_float(0x7f800000),
+                n_box, n_obj, smem_base);
+            if (best.node != 0xffffffffu) cls = P.R.scene.object_class[best.node];
+            entry = make_uint4((uint32_t)at, __float_as_uint(best.t), best.node, 0u);
         }
+        const uint32_t j = queue_reserve(P.hit_count, valid, cls);
+        if (valid) P.hitq[(size_t)cls * P.capacity + j] = entry;
     }
     if (COUNT) {
         warp_add(&P.R.counters[0], n_rays);
@@ -192,65 +217,57 @@ __global__ void __launch_bounds__(256) wf_extend(const WfParams P) {
     }
 }
 
+// One thread per hit record; every 256-record chunk belongs to one shading class.
 template <bool COUNT, bool QUADS>
 __global__ void __launch_bounds__(256) wf_shade(const WfParams P) {
-    __shared__ uint32_t s_first[kOctants + 1];
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (uint32_t o = 0; o < kOctants; ++o) {
-            s_first[o] = acc;
-            acc += P.count_in[o];
-        }
-        s_first[kOctants] = acc;
-    }
-    __syncthreads();
-    const uint32_t n = s_first[kOctants];
-    const uint32_t stride = gridDim.x * blockDim.x;
+    __shared__ ChunkMap map;
+    chunk_map_init(map, P.hit_count, kShadeClasses);
+    const uint32_t total_chunks = map.first_chunk[kBins];
     uint32_t n_hits = 0;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
-        const uint32_t g = base + threadIdx.x;
+    for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+        uint32_t cls = 0;
+        while (c >= map.first_chunk[cls + 1u]) ++cls;
+        const uint32_t i = (c - map.first_chunk[cls]) * kChunk + threadIdx.x;
         bool push = false;
         DRay next;
         next.o = next.d = f3(0.f, 0.f, 0.f);
         next.time = 0.f;
         uint32_t slot = 0;
-        if (g < n) {
-            uint32_t oct = 0;
-            while (g >= s_first[oct + 1u]) ++oct;
-            const size_t at = (size_t)oct * P.capacity + (g - s_first[oct]);
-            const float4 a = P.in.o_time[at];
-            const float4 b = P.in.d_slot[at];
+        if (i < map.count[cls]) {
+            const uint4 e = P.hitq[(size_t)cls * P.capacity + i];
+            const float4 a = P.in.rays[2u * (size_t)e.x];
+            const float4 b = P.in.rays[2u * (size_t)e.x + 1u];
             DRay r;
             r.o = f3(a);
             r.time = a.w;
             r.d = f3(b);
             slot = __float_as_uint(b.w);
-            const float2 h = P.hits[at];
-            Nearest best;
-            best.t = h.x;
-            best.node = __float_as_uint(h.y);
-            float3 L = f3(P.L[slot]);
-            const float3 T = f3(P.T[slot]);
-            if (best.node == 0xffffffffu) {
+            const float4 tl0 = P.TL[2u * (size_t)slot];
+            const float4 tl1 = P.TL[2u * (size_t)slot + 1u];
+            float3 T = f3(tl0);
+            float3 L = f3(tl0.w, tl1.x, tl1.y);
+            if (cls == CLASS_MISS) {  // block-uniform
                 L = L + T * miss_color(P.R.cam, r);
             } else {
                 if (COUNT) ++n_hits;
+                const float4* __restrict__ pr = P.R.scene.prims + 4u * (size_t)e.z;
+                const float4 f0 = pr[0], f1 = pr[1], m0 = pr[2], m1 = pr[3];
                 uint32_t pixel;
                 slot_pixel(P.R, slot % P.slots_per_sample, pixel);
                 RngKey key;
                 key.seed = P.R.seed;
                 key.pixel = pixel;
                 key.sample = P.batch_begin + slot / P.slots_per_sample;
-                const ShadeResult sr = shade<QUADS>(P.R.scene, P.R.scene.prims, r, best, key, P.segment);
+                const ShadeResult sr = shade_rec<QUADS>(P.R.scene, f0, f1, m0, m1, r, __uint_as_float(e.y), key, P.segment);
                 L = L + T * sr.emitted;
                 if (sr.scatters && P.segment < P.R.cam.max_depth) {
-                    const float3 Tn = T * sr.attenuation;
-                    P.T[slot] = make_float4(Tn.x, Tn.y, Tn.z, 0.f);
+                    T = T * sr.attenuation;
                     next = sr.scattered;
                     push = true;
                 }
             }
-            P.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
+            P.TL[2u * (size_t)slot] = make_float4(T.x, T.y, T.z, L.x);
+            P.TL[2u * (size_t)slot + 1u] = make_float4(L.y, L.z, 0.f, 0.f);
         }
         push_ray(P, next, slot, push);
     }
@@ -264,10 +281,12 @@ __global__ void __launch_bounds__(256) wf_accumulate(const WfParams P) {
     if (!slot_pixel(P.R, r, pixel)) return;
     float4 acc = P.R.accum[pixel];
     for (uint32_t b = 0; b < P.batch_samples; ++b) {
-        const float4 l = P.L[(size_t)b * P.slots_per_sample + r];
-        acc.x += l.x;
-        acc.y += l.y;
-        acc.z += l.z;
+        const size_t s = (size_t)b * P.slots_per_sample + r;
+        const float4 tl0 = P.TL[2u * s];
+        const float4 tl1 = P.TL[2u * s + 1u];
+        acc.x += tl0.w;
+        acc.y += tl1.x;
+        acc.z += tl1.y;
     }
     acc.w = (float)(P.batch_begin + P.batch_samples);
     P.R.accum[pixel] = acc;
@@ -278,15 +297,13 @@ WavefrontState* wavefront_create() { return new (std::nothrow) WavefrontState();
 
 static void lane_free(WfLane* ln) {
     for (int k = 0; k < 2; ++k) {
-        cudaFree(ln->q[k].o_time);
-        cudaFree(ln->q[k].d_slot);
+        cudaFree(ln->q[k].rays);
         ln->q[k] = WfQueue{};
     }
-    cudaFree(ln->hits);
-    cudaFree(ln->T);
-    cudaFree(ln->L);
-    ln->hits = nullptr;
-    ln->T = ln->L = nullptr;
+    cudaFree(ln->hitq);
+    cudaFree(ln->TL);
+    ln->hitq = nullptr;
+    ln->TL = nullptr;
     ln->capacity = 0;
 }
 
@@ -311,7 +328,7 @@ static cudaError_t wf_init(WavefrontState* st) {
     for (WfLane& ln : st->lanes) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.accumulated, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaMalloc(&ln.counts, 2 * kOctants * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&ln.counts, 4 * kBins * sizeof(uint32_t));
     }
     st->ready = e == cudaSuccess;
     return e;
@@ -323,12 +340,10 @@ static cudaError_t lane_reserve(WfLane* ln, size_t capacity) {
     if (e != cudaSuccess) return e;
     lane_free(ln);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-        e = cudaMalloc(&ln->q[k].o_time, kOctants * capacity * sizeof(float4));
-        if (e == cudaSuccess) e = cudaMalloc(&ln->q[k].d_slot, kOctants * capacity * sizeof(float4));
+        e = cudaMalloc(&ln->q[k].rays, 2 * kOctants * capacity * sizeof(float4));
     }
-    if (e == cudaSuccess) e = cudaMalloc(&ln->hits, kOctants * capacity * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMalloc(&ln->T, capacity * sizeof(float4));
-    if (e == cudaSuccess) e = cudaMalloc(&ln->L, capacity * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&ln->hitq, kShadeClasses * capacity * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(&ln->TL, 2 * capacity * sizeof(float4));
     if (e != cudaSuccess) {
         lane_free(ln);
         return e;
@@ -340,7 +355,7 @@ static cudaError_t lane_reserve(WfLane* ln, size_t capacity) {
 template <bool COUNT, bool QUADS>
 static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
     if (smem_nodes) {
-        const size_t smem = (size_t)P.R.scene.n_nodes * 32u;
+        const size_t smem = ((size_t)P.R.scene.n_nodes + 1u) * 32u;
         auto k = wf_extend<true, COUNT, QUADS>;
         if (smem > 40u * 1024u) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -370,12 +385,12 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     cudaError_t e = wf_init(st);
     if (e != cudaSuccess) return e;
     const uint32_t slots_per_sample = owned * kCtaThreads;
-    // Samples in flight per pixel and batch (608 B of queue/state per path: 4.9 GB per lane at 8 M).
+    // Samples in flight per pixel and batch (624 B of queue/state per path slot: 5.2 GB per lane at 8 M).
     const uint64_t target_paths = 8ull << 20;
     uint32_t B = (uint32_t)((target_paths + slots_per_sample - 1) / slots_per_sample);
     if (B < 1u) B = 1u;
     if (B > p.sample_count) B = p.sample_count;
-    if ((uint64_t)B * slots_per_sample > 0x3fffffffull) B = (uint32_t)(0x3fffffffull / slots_per_sample);
+    if ((uint64_t)B * slots_per_sample > 0x1fffffffull) B = (uint32_t)(0x1fffffffull / slots_per_sample);
     if (B < 1u) return cudaErrorInvalidValue;
     const uint32_t n_batches = (p.sample_count + B - 1u) / B;
     const int lanes_used = n_batches < (uint32_t)kLanes ? (int)n_batches : kLanes;
@@ -384,7 +399,8 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         if (e != cudaSuccess) return e;
     }
 
-    const bool smem_nodes = p.scene.n_nodes > 0 && (size_t)p.scene.n_nodes * 32u <= megakernel_max_smem_nodes_bytes();
+    const bool smem_nodes =
+        p.scene.n_nodes > 0 && ((size_t)p.scene.n_nodes + 1u) * 32u <= megakernel_max_smem_nodes_bytes();
     const bool quads = p.scene.has_quads != 0u;
     const uint32_t max_grid = (uint32_t)st->sm_count * 8u;
 
@@ -404,27 +420,28 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         WfParams P{};
         P.R = p;
         P.R.tile_world = world;
-        P.hits = ln.hits;
-        P.T = ln.T;
-        P.L = ln.L;
+        P.hitq = ln.hitq;
+        P.TL = ln.TL;
         P.capacity = (uint32_t)ln.capacity;
         P.slots_per_sample = slots_per_sample;
         P.batch_begin = p.sample_begin + s0;
         P.batch_samples = nb;
-        e = cudaMemsetAsync(ln.counts, 0, 2 * kOctants * sizeof(uint32_t), ln.stream);
+        e = cudaMemsetAsync(ln.counts, 0, 4 * kBins * sizeof(uint32_t), ln.stream);
         if (e != cudaSuccess) return e;
         int cur = 0;
         P.out = ln.q[cur];
-        P.count_out = ln.counts + cur * kOctants;
-        uint32_t grid = (cap + 255u) / 256u + kOctants;  // chunks: every bin may end with a partial one
+        P.count_out = ln.counts + cur * kBins;
+        uint32_t grid = (cap + 255u) / 256u + kBins;  // chunks: every bin may end with a partial one
         if (grid > max_grid) grid = max_grid;
         wf_raygen<<<grid, 256, 0, ln.stream>>>(P);
         ++launches;
         for (uint32_t bounce = 0; bounce < p.cam.max_depth; ++bounce) {
             P.in = ln.q[cur];
-            P.count_in = ln.counts + cur * kOctants;
+            P.count_in = ln.counts + cur * kBins;
             P.out = ln.q[cur ^ 1];
-            P.count_out = ln.counts + (cur ^ 1) * kOctants;
+            P.count_out = ln.counts + (cur ^ 1) * kBins;
+            P.hit_count = ln.counts + (2u + (bounce & 1u)) * kBins;
+            P.hit_count_next = ln.counts + (2u + ((bounce + 1u) & 1u)) * kBins;
             P.segment = bounce + 1u;
 #define RTB_WF(C, Q)                                                      \
     do {                                                                  \
