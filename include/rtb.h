@@ -327,6 +327,13 @@ int rtb_job_destroy(RtbJob* job);
 int rtb_philox_device_selftest(const uint32_t* counters4, const uint32_t* key2, uint32_t n,
                                uint32_t* out4, int device);
 
+/* Test hook (no device needed): the library's host-side re-layout of the scene's tree for traversal mode
+ * `mode` (RTB_TRAVERSAL_*) and ray octant 0..7, as 8 floats per node — {entry.xyz | center1.xyz, bits(meta)},
+ * {exit.xyz | center_vec.xyz, radius} — with the end sentinel at index *n_nodes_out.  out_nodes may be NULL
+ * to query the node count; otherwise it must hold 8 * (n_nodes + 1) floats. */
+int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, uint32_t octant, float* out_nodes,
+                           uint32_t* n_nodes_out);
+
 /* Measurement aid for the roofline: runs a dependent-chain FFMA microbenchmark (8 independent chains
  * per thread, full grid) on `device` and returns the best-of-5 rate in TFLOP/s counting one FMA as two
  * flops.  The path tracer itself is compiled without multiply-add contraction, so its own ceiling is

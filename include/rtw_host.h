@@ -23,7 +23,10 @@ enum {
     RTW_SCENE_TWO_SPHERES = 2,   /* twoSpheresWorld     src/main.zig:101-113 */
     RTW_SCENE_TWO_PERLIN = 3,    /* twoPerlinWorld      src/main.zig:115-125 */
     RTW_SCENE_TEXTURED = 4,      /* BASELINE config 3: checker + earth + perlin in one world */
-    RTW_SCENE_RANDOM_SPHERES = 5 /* BASELINE config 4: n random spheres + ground            */
+    RTW_SCENE_RANDOM_SPHERES = 5, /* BASELINE config 4: n random spheres + ground            */
+    RTW_SCENE_QUADS = 6,          /* quadsWorld          src/main.zig:127-143 */
+    RTW_SCENE_SIMPLE_LIGHT = 7    /* simpleLightWorld    src/main.zig:145-166 (camera: lookfrom (26,3,6), lookat
+                                     (0,2,0), depth 50, defocus 0, black background) */
 };
 enum {
     RTW_BOOK1_CHECKER_GROUND = 1u << 0, /* HEAD's checker ground (main.zig:257-260) instead of Book-1 grey */

@@ -1,0 +1,124 @@
+"""CPU tests of the library's host-side scene re-layout (rtb_debug_build_layout — no device needed): the threaded
+per-octant node arrays the kernels walk, for all three traversal modes.  A plain-Python walker applies the kernels'
+rules (slab test on pre-swapped planes, skip links, end sentinel) and must find the oracle's hits."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+END = 0xFFFFFFFF
+
+
+def _layout(pkg, world, mode, octant):
+    n = C.c_uint32(0)
+    assert pkg._ffi.rtb().rtb_debug_build_layout(world.desc, mode, octant, None, C.byref(n)) == 0
+    out = np.zeros((n.value + 1, 8), np.float32)
+    assert pkg._ffi.rtb().rtb_debug_build_layout(world.desc, mode, octant, out.ctypes.data, C.byref(n)) == 0
+    return out, n.value
+
+
+@pytest.mark.parametrize("scene", ["book1", "quads", "textured"])
+def test_layout_invariants(pkg, scene, earthmap):
+    world = {"book1": lambda: pkg.World.book1(), "quads": lambda: pkg.World.create(pkg.RTW_SCENE_QUADS),
+             "textured": lambda: pkg.World.create(pkg.RTW_SCENE_TEXTURED, image=earthmap)}[scene]()
+    d = world.desc.contents
+    ref_boxes = None
+    for mode in (0, 1, 2):
+        for octant in range(8):
+            L, n = _layout(pkg, world, mode, octant)
+            assert n == d.n_nodes
+            meta = L[:, 3].view(np.uint32)
+            assert meta[n] == END                                       # the sentinel closes every octant
+            kind, idx = meta[:n] >> 30, meta[:n] & 0x3FFFFFFF
+            leaves = kind != 0
+            assert sorted(idx[leaves].tolist()) == list(range(d.n_hittables))   # every object exactly once
+            inner = np.nonzero(~leaves)[0]
+            assert (idx[inner] > inner + 2).all() and (idx[inner] <= n).all()   # skip jumps over >= 2 children
+            # pre-swapped slabs: entry plane = max where the octant bit is set, min otherwise
+            for a in range(3):
+                lo, hi = L[inner, a], L[inner, 4 + a]
+                assert (hi <= lo).all() if (octant >> a) & 1 else (lo <= hi).all()
+            # skip(i) = end of i's subtree: the subtree of i is exactly [i, skip(i)) and nests properly
+            for i in inner[:200]:
+                sub = np.arange(i + 1, idx[i])
+                inner_sub = sub[kind[sub] == 0]
+                assert (idx[inner_sub] <= idx[i]).all()
+            # every octant of a mode holds the same set of boxes (only swapped / reordered)
+            boxes = sorted(map(tuple, np.concatenate([np.minimum(L[inner, :3], L[inner, 4:7]),
+                                                      np.maximum(L[inner, :3], L[inner, 4:7])], axis=1).tolist()))
+            if octant == 0:
+                ref_boxes = boxes
+            assert boxes == ref_boxes
+
+
+def _walk(L, n, hittables, ray):
+    """The kernels' traverse_octant, in Python (float32 arithmetic via numpy scalars)."""
+    f = np.float32
+    o, d, time = ray["origin"].astype(f), ray["direction"].astype(f), f(ray["time"])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = f(1) / d
+        best_t, best_obj = f(np.inf), -1
+        tmin = f(0.001)
+        a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+        i, n_box = 0, 0
+        meta = L[:, 3].view(np.uint32)
+        while True:
+            m = int(meta[i])
+            if m < (1 << 30):
+                n_box += 1
+                t0 = (L[i, :3] - o) * inv
+                t1 = (L[i, 4:7] - o) * inv
+                lo = max(np.fmax.reduce(t0), tmin)      # fmax/fmin ignore NaN like PTX max/min
+                hi = min(np.fmin.reduce(t1), best_t)
+                i = m if hi <= lo else i + 1
+                continue
+            if m == END:
+                break
+            kind, obj = m >> 30, m & 0x3FFFFFFF
+            if kind != 3:
+                c = L[i, :3] + (time * L[i, 4:7] if kind == 2 else f(0))
+                oc = o - c
+                hb = oc[0] * d[0] + oc[1] * d[1] + oc[2] * d[2]
+                cc = (oc[0] * oc[0] + oc[1] * oc[1] + oc[2] * oc[2]) - L[i, 7] * L[i, 7]
+                disc = hb * hb - a * cc
+                if disc >= 0:
+                    s = np.sqrt(disc)
+                    root = (-hb - s) / a
+                    if not (tmin < root < best_t):
+                        root = (-hb + s) / a
+                    if tmin < root < best_t:
+                        best_t, best_obj = root, obj
+            i += 1
+    return best_obj, best_t, n_box
+
+
+def test_python_walk_of_every_layout_finds_the_oracle_hits(pkg, orc):
+    world = pkg.World.book1()
+    d = world.desc.contents
+    cam = pkg.book1_camera(400, 10, 50).init()
+    rng = np.random.default_rng(3)
+    rays = orc.get_rays(cam, 9, rng.integers(0, 400 * 225, 120), 0)
+    extra = np.zeros(120, dtype=rays.dtype)
+    extra["origin"] = rng.uniform(-8, 8, (120, 3)).astype(np.float32)
+    extra["origin"][:, 1] = np.abs(extra["origin"][:, 1]) * 0.2 + 0.05
+    extra["direction"] = rng.normal(size=(120, 3)).astype(np.float32)
+    extra["time"] = rng.random(120).astype(np.float32)
+    extra["t_min"], extra["t_max"] = 0.001, np.inf
+    rays = np.concatenate([rays, extra])
+    cpu = orc.trace_rays(world.desc, rays)
+    layouts = {(m, o): _layout(pkg, world, m, o) for m in (0, 1, 2) for o in range(8)}
+    total = {0: 0, 1: 0, 2: 0}
+    for k, ray in enumerate(rays):
+        with np.errstate(divide="ignore"):
+            inv = np.float32(1) / ray["direction"]
+        octant = int(inv[0] < 0) | (int(inv[1] < 0) << 1) | (int(inv[2] < 0) << 2)
+        for mode in (0, 1, 2):
+            L, n = layouts[(mode, octant)]
+            obj, t, n_box = _walk(L, n, d.hittables, ray)
+            assert obj == cpu["object"][k], (k, mode)
+            if obj >= 0:
+                assert np.float32(t) == cpu["t"][k]
+            if mode == 0:
+                assert n_box == cpu["n_box_tests"][k]      # reference order: the very same node visits
+            total[mode] += n_box
+    assert total[1] <= total[0] and total[2] < 0.6 * total[0]   # SAH re-partition: far fewer slab tests

@@ -325,6 +325,12 @@ def textured_camera(width=800, spp=256, max_depth=50):
                   lookat=(0.0, 2.0, 0.0), vfov=35.0, defocus_angle=0.0, background=(0.70, 0.80, 1.00))
 
 
+def simple_light_camera(width=800, spp=100, max_depth=50):
+    """simpleLightWorld's camera overrides (src/main.zig:156-161); HEAD's black background (src/camera.zig:80)."""
+    return Camera(image_width=width, samples_per_pixel=spp, max_depth=max_depth, lookfrom=(26.0, 3.0, 6.0),
+                  lookat=(0.0, 2.0, 0.0), vup=(0.0, 1.0, 0.0), defocus_angle=0.0)
+
+
 def million_camera(width=3840, spp=64, max_depth=50):
     return Camera(image_width=width, samples_per_pixel=spp, max_depth=max_depth, lookfrom=(520.0, 80.0, 120.0),
                   lookat=(0.0, 10.0, 0.0), vfov=40.0, defocus_angle=0.0, background=(0.70, 0.80, 1.00))

@@ -33,7 +33,7 @@ RTB_TRAVERSAL_REFERENCE, RTB_TRAVERSAL_ORDERED, RTB_TRAVERSAL_SAH = 0, 1, 2
 RTB_FLAG_COUNT_WORK = 1
 
 RTW_SCENE_BOOK1, RTW_SCENE_EARTH, RTW_SCENE_TWO_SPHERES, RTW_SCENE_TWO_PERLIN, RTW_SCENE_TEXTURED, \
-    RTW_SCENE_RANDOM_SPHERES = range(6)
+    RTW_SCENE_RANDOM_SPHERES, RTW_SCENE_QUADS, RTW_SCENE_SIMPLE_LIGHT = range(8)
 RTW_BOOK1_CHECKER_GROUND, RTW_BOOK1_EARTH_SPHERE, RTW_BOOK1_STATIC_SPHERES = 1, 2, 4
 
 f32, u32, i32, u64, u16, u8 = C.c_float, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint16, C.c_uint8
@@ -129,7 +129,7 @@ RTB_SYMBOLS = [
     "rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_scene_create", "rtb_scene_destroy",
     "rtb_trace_rays", "rtb_render", "rtb_render_device", "rtb_resolve_device", "rtb_resolve", "rtb_render_async",
     "rtb_job_progress", "rtb_job_cancel", "rtb_job_wait", "rtb_job_destroy", "rtb_philox_device_selftest",
-    "rtb_measure_fp32_peak",
+    "rtb_measure_fp32_peak", "rtb_debug_build_layout",
 ]
 RTW_SYMBOLS = [
     "rtw_world_create", "rtw_world_new", "rtw_world_add_image", "rtw_world_add_sphere", "rtw_world_add_quad",
@@ -176,6 +176,7 @@ def rtb() -> C.CDLL:
     lib.rtb_job_destroy.argtypes = [vp]
     lib.rtb_philox_device_selftest.argtypes = [vp, vp, u32, vp, C.c_int]
     lib.rtb_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.rtb_debug_build_layout.argtypes = [C.POINTER(RtbSceneDesc), u32, u32, vp, C.POINTER(u32)]
     for s in RTB_SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("rtb_abi_version", "rtb_last_error"):

@@ -581,6 +581,42 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     return RTB_OK;
 }
 
+// Test hook: the host-side re-layout of one (mode, octant) without touching a device, so that the CPU
+// test-suite can check the threaded layouts (skip links, sentinel, every object exactly once, boxes).
+extern "C" int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, uint32_t octant, float* out_nodes,
+                                      uint32_t* n_nodes_out) {
+    int rc = validate_desc(desc);
+    if (rc != RTB_OK) return rc;
+    if (mode > RTB_TRAVERSAL_SAH || octant > 7 || !n_nodes_out) return fail(RTB_ERR_INVALID_ARGUMENT, "bad mode/octant");
+    std::vector<uint32_t> size;
+    uint32_t depth = 0;
+    rc = tree_sizes(desc, size, &depth);
+    if (rc != RTB_OK) return rc;
+    std::vector<uint32_t> quad_slot(desc->n_hittables, 0);
+    uint32_t n_quads = 0;
+    for (uint32_t i = 0; i < desc->n_hittables; ++i)
+        if (desc->hittables[i].type == RTB_HITTABLE_QUAD) quad_slot[i] = n_quads++;
+    const uint32_t n_tree = desc->n_nodes ? size[desc->root] : 0u;
+    *n_nodes_out = n_tree;
+    if (!out_nodes) return RTB_OK;
+    std::vector<float4> layout(2 * ((size_t)n_tree + 1), mkf4(0.0f, 0.0f, 0.0f, bits(RTB_META_END)));
+    if (mode == RTB_TRAVERSAL_SAH) {
+        std::vector<RtbBvhNode> sah_nodes;
+        RtbSceneDesc sah = *desc;
+        sah.root = build_sah(desc, size, sah_nodes);
+        sah.nodes = sah_nodes.data();
+        sah.n_nodes = (uint32_t)sah_nodes.size();
+        std::vector<uint32_t> sah_size;
+        rc = tree_sizes(&sah, sah_size, &depth);
+        if (rc != RTB_OK) return rc;
+        emit_layout(&sah, sah_size, quad_slot, (int)octant, true, layout.data());
+    } else {
+        emit_layout(desc, size, quad_slot, (int)octant, mode == RTB_TRAVERSAL_ORDERED, layout.data());
+    }
+    std::memcpy(out_nodes, layout.data(), layout.size() * sizeof(float4));
+    return RTB_OK;
+}
+
 extern "C" int rtb_scene_destroy(RtbScene* scene) {
     if (!scene) return RTB_OK;
     scene_free(scene);

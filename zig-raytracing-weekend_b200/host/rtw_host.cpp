@@ -530,6 +530,27 @@ World twoPerlinWorld(HostRng& perlin_rng, HostRng& bvh_rng) {
     return finishWorld(std::move(objs), bvh_rng, {});
 }
 
+World quadsWorld(HostRng& bvh_rng) {  // main.zig:127-143
+    ObjectList objs;
+    objs.push_back(Quad::init({-3, -2, 5}, {0, 0, -4}, {0, 4, 0}, Lambertian::fromColor({1, 0.2f, 0.2f})));
+    objs.push_back(Quad::init({-2, -2, 0}, {4, 0, 0}, {0, 4, 0}, Lambertian::fromColor({0.2f, 1.0f, 0.2f})));
+    objs.push_back(Quad::init({3, -2, 1}, {0, 0, 4}, {0, 4, 0}, Lambertian::fromColor({0.2f, 0.2f, 1.0f})));
+    objs.push_back(Quad::init({-2, -3, 1}, {4, 0, 0}, {0, 0, 4}, Lambertian::fromColor({1.0f, 0.5f, 0})));
+    objs.push_back(Quad::init({-2, -3, 5}, {4, 0, 0}, {0, 0, -4}, Lambertian::fromColor({0.2f, 0.8f, 0.8f})));
+    return finishWorld(std::move(objs), bvh_rng, {});
+}
+
+World simpleLightWorld(HostRng& perlin_rng, HostRng& bvh_rng) {  // main.zig:145-166
+    const Material material = Lambertian::init(NoiseTexture::init(4, perlin_rng));
+    ObjectList objs;
+    objs.push_back(Sphere::init({0, -1000, 0}, 1000, material));
+    objs.push_back(Sphere::init({0, 2, 0}, 2, material));
+    const Material difflight = DiffuseLight::fromColor({4, 4, 4});
+    objs.push_back(Quad::init({3, 1, -2}, {2, 0, 0}, {0, 2, 0}, difflight));
+    objs.push_back(Sphere::init({0, 7, 0}, 2, difflight));
+    return finishWorld(std::move(objs), bvh_rng, {});
+}
+
 World texturedWorld(HostRng& perlin_rng, HostRng& bvh_rng, std::vector<Image> images) {
     const Material perlin = Lambertian::init(NoiseTexture::init(4, perlin_rng));
     const Texture checker =

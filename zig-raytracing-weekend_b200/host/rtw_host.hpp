@@ -222,6 +222,8 @@ World generateWorld(HostRng& scene_rng, HostRng& bvh_rng, const Book1Options& op
 World earthWorld(HostRng& bvh_rng, std::vector<Image> images);           // main.zig:88-99
 World twoSpheresWorld(HostRng& bvh_rng);                                 // main.zig:101-113
 World twoPerlinWorld(HostRng& perlin_rng, HostRng& bvh_rng);             // main.zig:115-125
+World quadsWorld(HostRng& bvh_rng);                                      // main.zig:127-143
+World simpleLightWorld(HostRng& perlin_rng, HostRng& bvh_rng);           // main.zig:145-166
 // BASELINE config 3: the three textured worlds side by side in one BVH.
 World texturedWorld(HostRng& perlin_rng, HostRng& bvh_rng, std::vector<Image> images);
 // BASELINE config 4: n random spheres (80/15/5 % lambertian/metal/dielectric) + ground sphere.

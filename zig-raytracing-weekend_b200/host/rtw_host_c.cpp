@@ -61,6 +61,12 @@ extern "C" int rtw_world_create(const RtwSceneParams* p, RtwWorld** out) {
         case RTW_SCENE_RANDOM_SPHERES:
             w->world = randomSpheresWorld(scene_rng, bvh_rng, p->n_spheres);
             break;
+        case RTW_SCENE_QUADS:
+            w->world = quadsWorld(bvh_rng);
+            break;
+        case RTW_SCENE_SIMPLE_LIGHT:
+            w->world = simpleLightWorld(perlin_rng, bvh_rng);
+            break;
         default:
             return RTB_ERR_INVALID_ARGUMENT;
     }
