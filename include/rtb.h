@@ -45,7 +45,7 @@ typedef enum RtbStatus {
 /* Hittable variants lowered from the tagged union at src/objects.zig:39-47.
  * LIST/TRANSLATE/ROTATE_Y/CONSTANT_MEDIUM are SURVEY §8(f) "next" rows; RoundBox is unfinished
  * in the reference (src/objects.zig:171-192) and has no tag. */
-enum { RTB_HITTABLE_SPHERE = 0, RTB_HITTABLE_QUAD = 1 };
+enum { RTB_HITTABLE_SPHERE = 0, RTB_HITTABLE_QUAD = 1, RTB_HITTABLE_BOX = 2 };
 
 /* Material variants, src/material.zig:11-16. */
 enum {
@@ -63,8 +63,13 @@ enum { RTB_TEX_SOLID = 0, RTB_TEX_CHECKER = 1, RTB_TEX_IMAGE = 2, RTB_TEX_NOISE 
  * position in RtbSceneDesc.hittables is the "object index" reported by rtb_trace_rays.
  *   sphere (src/objects.zig:68-75): a = center1, b = center_vec (zero unless is_moving), radius
  *   quad   (src/objects.zig:195-204): a = q, b = u, c = v
+ *   box    = Translate(RotateY(createBox(a, b, material), angle), c) as one world object, the way
+ *            cornellBox builds its two boxes (src/main.zig:182-190): a, b = the corners handed to
+ *            createBox (src/objects.zig:510-532, a HittableList of 6 quads), sin_theta / cos_theta =
+ *            RotateY's fields (src/objects.zig:350-358; 0 / 1 when there is no RotateY), c =
+ *            Translate.offset (src/objects.zig:309; zero when there is no Translate).
  * The bounding box is not carried here: the BVH nodes hold the boxes the host computed
- * (Sphere.init / initMoving, src/objects.zig:80-92). */
+ * (Sphere.init / initMoving, src/objects.zig:80-92; RotateY.init :360-397; Translate.init :314-319). */
 typedef struct RtbHittable {
     uint32_t type;      /* RTB_HITTABLE_* */
     uint32_t material;  /* index into RtbSceneDesc.materials (the reference stores Material by value) */
@@ -73,8 +78,10 @@ typedef struct RtbHittable {
     float a[3];
     float b[3];
     float c[3];
+    float sin_theta; /* box only */
+    float cos_theta; /* box only */
     uint32_t reserved;
-} RtbHittable; /* 56 bytes */
+} RtbHittable; /* 64 bytes */
 
 /* src/material.zig:32-144.
  *   lambertian:    texture = albedo texture          (:33)

@@ -25,8 +25,11 @@ enum {
     RTW_SCENE_TEXTURED = 4,      /* BASELINE config 3: checker + earth + perlin in one world */
     RTW_SCENE_RANDOM_SPHERES = 5, /* BASELINE config 4: n random spheres + ground            */
     RTW_SCENE_QUADS = 6,          /* quadsWorld          src/main.zig:127-143 */
-    RTW_SCENE_SIMPLE_LIGHT = 7    /* simpleLightWorld    src/main.zig:145-166 (camera: lookfrom (26,3,6), lookat
+    RTW_SCENE_SIMPLE_LIGHT = 7,   /* simpleLightWorld    src/main.zig:145-166 (camera: lookfrom (26,3,6), lookat
                                      (0,2,0), depth 50, defocus 0, black background) */
+    RTW_SCENE_CORNELL_BOX = 8     /* cornellBox          src/main.zig:168-205 — HEAD's selected scene (:422);
+                                     camera: 600 x 600, 200 spp, depth 200, vfov 40, lookfrom (278,278,-800),
+                                     lookat (278,278,0), defocus 0, black background */
 };
 enum {
     RTW_BOOK1_CHECKER_GROUND = 1u << 0, /* HEAD's checker ground (main.zig:257-260) instead of Book-1 grey */
@@ -69,6 +72,10 @@ int rtw_world_add_sphere(RtwWorld* world, const float center1[3], const float* c
                          const RtwMaterialSpec* material);
 int rtw_world_add_quad(RtwWorld* world, const float q[3], const float u[3], const float v[3],
                        const RtwMaterialSpec* material);
+/* Translate.init(RotateY.init(createBox(a, b, material), angle), offset) as one world object (src/main.zig:182-190);
+ * rotate = 0 skips RotateY, offset = NULL skips Translate (src/objects.zig:314-319, :354-397, :510-532). */
+int rtw_world_add_box(RtwWorld* world, const float a[3], const float b[3], int rotate, float angle_degrees,
+                      const float* offset_or_null, const RtwMaterialSpec* material);
 int rtw_world_build(RtwWorld* world, uint64_t bvh_seed); /* BVHTree.init + lowering */
 
 const RtbSceneDesc* rtw_world_desc(const RtwWorld* world); /* valid until rtw_world_destroy */

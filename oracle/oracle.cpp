@@ -178,8 +178,62 @@ bool sphereHit(const RtbHittable& s, const Ray& r, Interval ray_t, HitRecord& re
 }
 
 // Quad.init derived fields (objects.zig:206-211) + Quad.hit (:226-261)
+bool quadHitQUV(V3 q, V3 u, V3 v, uint32_t material, const Ray& r, Interval ray_t, HitRecord& rec);
+
 bool quadHit(const RtbHittable& qd, const Ray& r, Interval ray_t, HitRecord& rec) {
-    const V3 q = v3(qd.a), u = v3(qd.b), v = v3(qd.c);
+    return quadHitQUV(v3(qd.a), v3(qd.b), v3(qd.c), qd.material, r, ray_t, rec);
+}
+
+// createBox (objects.zig:510-532): the six quads of the HittableList, in the order they are added.  (As in
+// the reference, the z = min face appears twice — entries 0 and 2 — and there is no z = max face.)
+void boxFaces(V3 a, V3 b, V3 q[6], V3 u[6], V3 v[6]) {
+    const V3 mn = v3(std::fmin(a.x, b.x), std::fmin(a.y, b.y), std::fmin(a.z, b.z));
+    const V3 mx = v3(std::fmax(a.x, b.x), std::fmax(a.y, b.y), std::fmax(a.z, b.z));
+    const V3 dx = v3(mx.x - mn.x, 0, 0), dy = v3(0, mx.y - mn.y, 0), dz = v3(0, 0, mx.z - mn.z);
+    q[0] = v3(mn.x, mn.y, mn.z); u[0] = dx;  v[0] = dy;
+    q[1] = v3(mx.x, mn.y, mx.z); u[1] = -dz; v[1] = dy;
+    q[2] = v3(mx.x, mn.y, mn.z); u[2] = -dx; v[2] = dy;
+    q[3] = v3(mn.x, mn.y, mn.z); u[3] = dz;  v[3] = dy;
+    q[4] = v3(mn.x, mx.y, mx.z); u[4] = dx;  v[4] = -dz;
+    q[5] = v3(mn.x, mn.y, mn.z); u[5] = dx;  v[5] = dz;
+}
+
+// Translate.hit (objects.zig:326-345) around RotateY.hit (:404-442) around HittableList.hit (:286-304)
+// over createBox's quads.
+bool boxHit(const RtbHittable& bx, const Ray& r, Interval ray_t, HitRecord& rec) {
+    const V3 offset = v3(bx.c);
+    const float sin_theta = bx.sin_theta, cos_theta = bx.cos_theta;
+    const Ray moved{r.origin - offset, r.direction, r.time};  // Translate.hit :331
+    V3 origin = moved.origin, direction = moved.direction;    // RotateY.hit :410-419
+    origin.x = cos_theta * moved.origin.x - sin_theta * moved.origin.z;
+    origin.z = sin_theta * moved.origin.x + cos_theta * moved.origin.z;
+    direction.x = cos_theta * moved.direction.x - sin_theta * moved.direction.z;
+    direction.z = sin_theta * moved.direction.x + cos_theta * moved.direction.z;
+    const Ray rotated{origin, direction, r.time};
+    V3 q[6], u[6], v[6];
+    boxFaces(v3(bx.a), v3(bx.b), q, u, v);
+    bool hit = false;
+    float closest_so_far = ray_t.max;  // HittableList.hit :291-301
+    HitRecord h;
+    for (int f = 0; f < 6; ++f) {
+        HitRecord cand;
+        if (quadHitQUV(q[f], u[f], v[f], bx.material, rotated, Interval{ray_t.min, closest_so_far}, cand)) {
+            closest_so_far = cand.t;
+            h = cand;
+            hit = true;
+        }
+    }
+    if (!hit) return false;
+    rec = h;  // RotateY.hit :425-439
+    rec.p.x = cos_theta * h.p.x + sin_theta * h.p.z;
+    rec.p.z = -sin_theta * h.p.x + cos_theta * h.p.z;
+    rec.normal.x = cos_theta * h.normal.x + sin_theta * h.normal.z;
+    rec.normal.z = -sin_theta * h.normal.x + cos_theta * h.normal.z;
+    rec.p = rec.p + offset;  // Translate.hit :340
+    return true;
+}
+
+bool quadHitQUV(V3 q, V3 u, V3 v, uint32_t material, const Ray& r, Interval ray_t, HitRecord& rec) {
     const V3 n = cross(u, v);
     const V3 normal = unitVector(n);
     const float d = dot(normal, q);
@@ -197,7 +251,7 @@ bool quadHit(const RtbHittable& qd, const Ray& r, Interval ray_t, HitRecord& rec
     rec.v = beta;
     rec.t = t;
     rec.p = intersection;
-    rec.mat = qd.material;
+    rec.mat = material;
     setFaceNormal(rec, r, normal);
     return true;
 }
@@ -210,6 +264,8 @@ bool hittableHit(const RtbSceneDesc* sc, uint32_t index, const Ray& r, Interval 
         ok = sphereHit(h, r, ray_t, rec);
     else if (h.type == RTB_HITTABLE_QUAD)
         ok = quadHit(h, r, ray_t, rec);
+    else if (h.type == RTB_HITTABLE_BOX)
+        ok = boxHit(h, r, ray_t, rec);
     if (ok) rec.object = (int32_t)index;
     return ok;
 }
@@ -824,6 +880,47 @@ void orc_quad_bbox(const float q_[3], const float u_[3], const float v_[3], floa
             bmin[a] = lo[a] - padding;
             bmax[a] = hi[a] + padding;
         }
+    }
+}
+
+void orc_box_bbox(const float a_[3], const float b_[3], float sin_theta, float cos_theta, const float offset[3],
+                  float bmin[3], float bmax[3]) {
+    // createBox -> HittableList.add (objects.zig:274-277): the list's box starts as Aabb{} = [0,0]^3 and is
+    // united with every quad's (padded) box, so it always contains the origin.
+    V3 q[6], u[6], v[6];
+    boxFaces(v3(a_), v3(b_), q, u, v);
+    float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+    for (int f = 0; f < 6; ++f) {
+        float qmn[3], qmx[3];
+        const float qa[3] = {q[f].x, q[f].y, q[f].z}, ua[3] = {u[f].x, u[f].y, u[f].z}, va[3] = {v[f].x, v[f].y, v[f].z};
+        orc_quad_bbox(qa, ua, va, qmn, qmx);
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = std::fmin(mn[k], qmn[k]);
+            mx[k] = std::fmax(mx[k], qmx[k]);
+        }
+    }
+    // RotateY.init (objects.zig:360-397): the 8 corners, rotated
+    const float inf = kInfinity;
+    float rmin[3] = {inf, inf, inf}, rmax[3] = {-inf, -inf, -inf};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            for (int k = 0; k < 2; ++k) {
+                const float i_f = (float)i, j_f = (float)j, k_f = (float)k;
+                const float x = i_f * mx[0] + (1 - i_f) * mn[0];
+                const float y = j_f * mx[1] + (1 - j_f) * mn[1];
+                const float z = k_f * mx[2] + (1 - k_f) * mn[2];
+                const float newx = cos_theta * x + sin_theta * z;
+                const float newz = -sin_theta * x + cos_theta * z;
+                const float tester[3] = {newx, y, newz};
+                for (int c = 0; c < 3; ++c) {
+                    rmin[c] = std::fmin(rmin[c], tester[c]);
+                    rmax[c] = std::fmax(rmax[c], tester[c]);
+                }
+            }
+    // Aabb.fromPoints(min, max) then Translate.init: bbox.add(offset) (objects.zig:315, aabb.zig:51-57)
+    for (int c = 0; c < 3; ++c) {
+        bmin[c] = std::fmin(rmin[c], rmax[c]) + offset[c];
+        bmax[c] = std::fmax(rmin[c], rmax[c]) + offset[c];
     }
 }
 

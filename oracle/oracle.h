@@ -112,6 +112,10 @@ void orc_camera_init(const OrcCameraOptions* opt, RtbCamera* cam_out);
  * sphere), Quad.init incl. pad (:206-211, src/aabb.zig:36-43). */
 void orc_sphere_bbox(const float center1[3], const float* center2, float radius, float bmin[3], float bmax[3]);
 void orc_quad_bbox(const float q[3], const float u[3], const float v[3], float bmin[3], float bmax[3]);
+/* Translate(RotateY(createBox(a, b))) : HittableList.add (src/objects.zig:274-277, starts from Aabb{} = the
+ * origin), RotateY.init (:360-397), Translate.init (:314-319). */
+void orc_box_bbox(const float a[3], const float b[3], float sin_theta, float cos_theta, const float offset[3],
+                  float bmin[3], float bmax[3]);
 
 /* BVHTree.constructTree (src/bvh.zig:43-103): random axis, in-place heap sort of the object
  * slice (std.sort.heap restated), median split.  Permutes `hittables` and their boxes

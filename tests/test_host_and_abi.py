@@ -220,7 +220,7 @@ def test_libraries_export_every_declared_symbol(pkg):
 
 def test_pod_sizes_match_the_header(pkg):
     ffi = pkg._ffi
-    assert C.sizeof(ffi.RtbHittable) == 56 and C.sizeof(ffi.RtbMaterial) == 32 and C.sizeof(ffi.RtbTexture) == 48
+    assert C.sizeof(ffi.RtbHittable) == 64 and C.sizeof(ffi.RtbMaterial) == 32 and C.sizeof(ffi.RtbTexture) == 48
     assert C.sizeof(ffi.RtbBvhNode) == 40 and C.sizeof(ffi.RtbRay) == 36 and C.sizeof(ffi.RtbHit) == 52
     assert C.sizeof(ffi.RtbPerlin) == 256 * 12 + 3 * 512
     assert np.dtype(ffi.RAY_DTYPE).itemsize == 36 and np.dtype(ffi.HIT_DTYPE).itemsize == 52

@@ -146,6 +146,12 @@ class World:
         _check(_ffi.rtw().rtw_world_add_quad(self._h, C.byref(_vec3(q)), C.byref(_vec3(u)), C.byref(_vec3(v)),
                                              C.byref(spec)), "rtw_world_add_quad")
 
+    def add_box(self, a, b, spec, angle=None, offset=None):
+        """Translate.init(RotateY.init(createBox(a, b, mat), angle), offset); angle/offset None = not applied."""
+        off = C.byref(_vec3(offset)) if offset is not None else None
+        _check(_ffi.rtw().rtw_world_add_box(self._h, C.byref(_vec3(a)), C.byref(_vec3(b)), int(angle is not None),
+                                            float(angle or 0.0), off, C.byref(spec)), "rtw_world_add_box")
+
     def build(self, bvh_seed=2):
         _check(_ffi.rtw().rtw_world_build(self._h, bvh_seed), "rtw_world_build")
         return self
@@ -329,6 +335,12 @@ def simple_light_camera(width=800, spp=100, max_depth=50):
     """simpleLightWorld's camera overrides (src/main.zig:156-161); HEAD's black background (src/camera.zig:80)."""
     return Camera(image_width=width, samples_per_pixel=spp, max_depth=max_depth, lookfrom=(26.0, 3.0, 6.0),
                   lookat=(0.0, 2.0, 0.0), vup=(0.0, 1.0, 0.0), defocus_angle=0.0)
+
+
+def cornell_camera(width=600, spp=200, max_depth=200):
+    """cornellBox's camera (src/main.zig:191-200); HEAD's black background."""
+    return Camera(image_width=width, aspect_ratio=1.0, samples_per_pixel=spp, max_depth=max_depth, vfov=40.0,
+                  lookfrom=(278.0, 278.0, -800.0), lookat=(278.0, 278.0, 0.0), vup=(0.0, 1.0, 0.0), defocus_angle=0.0)
 
 
 def million_camera(width=3840, spp=64, max_depth=50):

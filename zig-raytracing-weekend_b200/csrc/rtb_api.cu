@@ -110,8 +110,34 @@ static inline float bits(uint32_t u) {
 }
 
 // Quad.init's derived fields (src/objects.zig:206-211), evaluated unfused in f32 on the host.
-static DevQuad make_quad(const RtbHittable& h) {
-    const float q[3] = {h.a[0], h.a[1], h.a[2]}, u[3] = {h.b[0], h.b[1], h.b[2]}, v[3] = {h.c[0], h.c[1], h.c[2]};
+static DevQuad make_quad_quv(const float q[3], const float u[3], const float v[3]);
+static DevQuad make_quad(const RtbHittable& h) { return make_quad_quv(h.a, h.b, h.c); }
+
+// Appends the table entries of one complex object and returns its slot: a quad is one entry; a box
+// (RTB_HITTABLE_BOX) is a header {offset, sin, cos} followed by createBox's six quads in its order
+// (src/objects.zig:510-532 — the z = min face twice, no z = max face, as in the reference).
+static uint32_t append_complex(std::vector<DevQuad>& table, const RtbHittable& h) {
+    const uint32_t slot = (uint32_t)table.size();
+    if (h.type == RTB_HITTABLE_QUAD) {
+        table.push_back(make_quad(h));
+        return slot;
+    }
+    DevQuad hdr{};
+    hdr.q_d = make_float4(h.c[0], h.c[1], h.c[2], h.sin_theta);
+    hdr.u = make_float4(h.cos_theta, 0.0f, 0.0f, 0.0f);
+    table.push_back(hdr);
+    const float mn[3] = {std::fmin(h.a[0], h.b[0]), std::fmin(h.a[1], h.b[1]), std::fmin(h.a[2], h.b[2])};
+    const float mx[3] = {std::fmax(h.a[0], h.b[0]), std::fmax(h.a[1], h.b[1]), std::fmax(h.a[2], h.b[2])};
+    const float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+    const float q[6][3] = {{mn[0], mn[1], mn[2]}, {mx[0], mn[1], mx[2]}, {mx[0], mn[1], mn[2]},
+                           {mn[0], mn[1], mn[2]}, {mn[0], mx[1], mx[2]}, {mn[0], mn[1], mn[2]}};
+    const float u[6][3] = {{ex, 0, 0}, {-0.0f, -0.0f, -ez}, {-ex, -0.0f, -0.0f}, {0, 0, ez}, {ex, 0, 0}, {ex, 0, 0}};
+    const float v[6][3] = {{0, ey, 0}, {0, ey, 0}, {0, ey, 0}, {0, ey, 0}, {-0.0f, -0.0f, -ez}, {0, 0, ez}};
+    for (int f = 0; f < 6; ++f) table.push_back(make_quad_quv(q[f], u[f], v[f]));
+    return slot;
+}
+
+static DevQuad make_quad_quv(const float q[3], const float u[3], const float v[3]) {
     const float n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
     const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
     const float normal[3] = {n[0] / len, n[1] / len, n[2] / len};
@@ -139,7 +165,7 @@ static int validate_desc(const RtbSceneDesc* d) {
         return fail(RTB_ERR_INVALID_ARGUMENT, "root %d out of range", d->root);
     for (uint32_t i = 0; i < d->n_hittables; ++i) {
         const RtbHittable& h = d->hittables[i];
-        if (h.type != RTB_HITTABLE_SPHERE && h.type != RTB_HITTABLE_QUAD)
+        if (h.type != RTB_HITTABLE_SPHERE && h.type != RTB_HITTABLE_QUAD && h.type != RTB_HITTABLE_BOX)
             return fail(RTB_ERR_UNSUPPORTED, "hittable %u: unsupported type %u", i, h.type);
         if (h.material >= d->n_materials) return fail(RTB_ERR_INVALID_ARGUMENT, "hittable %u: material out of range", i);
     }
@@ -219,7 +245,7 @@ static void leaf_record(const RtbSceneDesc* d, uint32_t object, const std::vecto
         *f1 = mkf4(h.b[0], h.b[1], h.b[2], h.radius);
     } else {
         *f0 = mkf4(0, 0, 0, bits((KIND_QUAD << 30) | object));
-        *f1 = mkf4(0, 0, 0, bits(quad_slot[object]));
+        *f1 = mkf4(bits(h.type == RTB_HITTABLE_BOX ? COMPLEX_BOX : COMPLEX_QUAD), 0, 0, bits(quad_slot[object]));
     }
 }
 
@@ -447,10 +473,7 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     std::vector<DevQuad> quads;
     std::vector<uint32_t> quad_slot(desc->n_hittables, 0);
     for (uint32_t i = 0; i < desc->n_hittables; ++i) {
-        if (desc->hittables[i].type == RTB_HITTABLE_QUAD) {
-            quad_slot[i] = (uint32_t)quads.size();
-            quads.push_back(make_quad(desc->hittables[i]));
-        }
+        if (desc->hittables[i].type != RTB_HITTABLE_SPHERE) quad_slot[i] = append_complex(quads, desc->hittables[i]);
     }
     const uint32_t n_tree = desc->n_nodes ? size[desc->root] : 0u;
     std::vector<float4> nodes(2 * (size_t)n_tree);
@@ -593,9 +616,9 @@ extern "C" int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, u
     rc = tree_sizes(desc, size, &depth);
     if (rc != RTB_OK) return rc;
     std::vector<uint32_t> quad_slot(desc->n_hittables, 0);
-    uint32_t n_quads = 0;
+    std::vector<DevQuad> table;
     for (uint32_t i = 0; i < desc->n_hittables; ++i)
-        if (desc->hittables[i].type == RTB_HITTABLE_QUAD) quad_slot[i] = n_quads++;
+        if (desc->hittables[i].type != RTB_HITTABLE_SPHERE) quad_slot[i] = append_complex(table, desc->hittables[i]);
     const uint32_t n_tree = desc->n_nodes ? size[desc->root] : 0u;
     *n_nodes_out = n_tree;
     if (!out_nodes) return RTB_OK;

@@ -257,6 +257,57 @@ __device__ __forceinline__ bool slab_miss(float4 f0, float4 f1, float3 o, float 
     return hi <= lo;
 }
 
+// A box instance = Translate(RotateY(createBox(a, b, mat), angle), offset) (src/objects.zig:308-443, :510-532),
+// stored in the quad table as a header entry {q_d = (offset.xyz, sin_theta), u.x = cos_theta} followed by
+// the 6 quads createBox makes, in its order.  Leaf record of a complex object: f1.x = bits(subtype).
+enum : uint32_t { COMPLEX_QUAD = 0u, COMPLEX_BOX = 1u };
+
+// Translate.hit (:331-335) then RotateY.hit (:410-421): the ray in the box's own frame.
+__device__ __forceinline__ DRay box_local_ray(const DRay& r, const DevQuad& hdr) {
+    const float3 offset = f3(hdr.q_d);
+    const float sin_theta = hdr.q_d.w, cos_theta = hdr.u.x;
+    const float3 mo = r.o - offset;
+    DRay l;
+    l.o = f3(cos_theta * mo.x - sin_theta * mo.z, mo.y, sin_theta * mo.x + cos_theta * mo.z);
+    l.d = f3(cos_theta * r.d.x - sin_theta * r.d.z, r.d.y, sin_theta * r.d.x + cos_theta * r.d.z);
+    l.time = r.time;
+    return l;
+}
+
+// HittableList.hit over the 6 faces (src/objects.zig:286-304): every face is tried with
+// ray_t.max = closest so far (inclusive for quads).  Returns the face index of the accepted hit.
+__device__ __forceinline__ bool box_root(const DRay& r, const DevQuad* __restrict__ entry, float t_min, float t_max,
+                                         float& t_out, uint32_t& face_out, float& alpha_out, float& beta_out) {
+    const DRay l = box_local_ray(r, entry[0]);
+    bool hit = false;
+    float closest = t_max;
+#pragma unroll 1
+    for (uint32_t f = 0; f < 6u; ++f) {
+        float t, alpha, beta;
+        if (quad_root(l, entry[1u + f], t_min, closest, t, alpha, beta)) {
+            closest = t;
+            hit = true;
+            t_out = t;
+            face_out = f;
+            alpha_out = alpha;
+            beta_out = beta;
+        }
+    }
+    return hit;
+}
+
+// Leaf test of a complex object (quad or box instance); f1 = {bits(subtype), -, -, bits(table slot)}.
+__device__ __forceinline__ bool complex_root(const DRay& r, const DevQuad* __restrict__ quads, float4 f1, float t_min,
+                                             float t_max, float& t_out) {
+    const DevQuad* __restrict__ entry = quads + __float_as_uint(f1.w);
+    float alpha, beta;
+    if (__float_as_uint(f1.x) == COMPLEX_BOX) {
+        uint32_t face;
+        return box_root(r, entry, t_min, t_max, t_out, face, alpha, beta);
+    }
+    return quad_root(r, entry[0], t_min, t_max, t_out, alpha, beta);
+}
+
 // Octant of a ray = the three `invD < 0` predicates of Aabb.hit (src/aabb.zig:97), bit k = axis k.
 __device__ __forceinline__ uint32_t ray_octant(float inv_x, float inv_y, float inv_z) {
     return (inv_x < 0.0f ? 1u : 0u) | (inv_y < 0.0f ? 2u : 0u) | (inv_z < 0.0f ? 4u : 0u);
@@ -353,8 +404,8 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
                 r.o = o;
                 r.d = d;
                 r.time = time;
-                float t, alpha, beta;
-                if (quad_root(r, quads[__float_as_uint(f1.w)], t_min, best.t, t, alpha, beta)) {
+                float t;
+                if (complex_root(r, quads, f1, t_min, best.t, t)) {
                     best.t = t;
                     best.node = meta & RTB_META_INDEX_MASK;
                 }
@@ -401,8 +452,8 @@ __device__ __forceinline__ Nearest traverse_reference(const float4* __restrict__
                     best.node = i;
                 }
             } else {
-                float t, alpha, beta;
-                if (quad_root(r, quads[__float_as_uint(f1.w)], t_min, best.t, t, alpha, beta)) {
+                float t;
+                if (complex_root(r, quads, f1, t_min, best.t, t)) {
                     best.t = t;
                     best.node = i;
                 }
@@ -449,6 +500,36 @@ __device__ __forceinline__ DHit finish_hit_rec(float4 f0, float4 f1, const DevQu
         const float3 center = (kind == KIND_MOVING_SPHERE) ? c1 + splat3(r.time) * f3(f1) : c1;
         outward = (h.p - center) / splat3(f1.w);
         if (WANT_UV) sphere_uv(outward, h.u, h.v);
+    } else if (__float_as_uint(f1.x) == COMPLEX_BOX) {
+        // Re-run the list test to learn which face was hit (same arithmetic, same t), build the record in the
+        // box's frame (Quad.hit :250-260), then rotate back (RotateY.hit :425-439) and translate (:338-342).
+        const DevQuad* __restrict__ entry = quads + __float_as_uint(f1.w);
+        const DRay l = box_local_ray(r, entry[0]);
+        // The list keeps the LAST face in createBox order whose root equals the final t (quads accept
+        // t == ray_t.max), so that is the face to rebuild; Interval [t, t] selects exactly those.
+        float alpha = 0.0f, beta = 0.0f;
+        uint32_t face = 0;
+#pragma unroll 1
+        for (uint32_t f = 0; f < 6u; ++f) {
+            float tt, a2, b2;
+            if (quad_root(l, entry[1u + f], t, t, tt, a2, b2)) {
+                face = f;
+                alpha = a2;
+                beta = b2;
+            }
+        }
+        const float3 lp = l.o + splat3(t) * l.d;
+        const float3 qn = f3(entry[1u + face].normal);
+        const bool front = dot3(l.d, qn) < 0.0f;
+        const float3 ln = front ? qn : -qn;
+        const float sin_theta = entry[0].q_d.w, cos_theta = entry[0].u.x;
+        const float3 offset = f3(entry[0].q_d);
+        h.p = f3(cos_theta * lp.x + sin_theta * lp.z, lp.y, -sin_theta * lp.x + cos_theta * lp.z) + offset;
+        h.normal = f3(cos_theta * ln.x + sin_theta * ln.z, ln.y, -sin_theta * ln.x + cos_theta * ln.z);
+        h.front_face = front;
+        h.u = alpha;
+        h.v = beta;
+        return h;
     } else {
         const DevQuad& qd = quads[__float_as_uint(f1.w)];
         outward = f3(qd.normal);

@@ -202,6 +202,66 @@ Hittable Quad::init(Vec3 q, Vec3 u, Vec3 v, const Material& mat) {
     return h;
 }
 
+// createBox (objects.zig:510-532) -> HittableList.add (:274-277): the list's box starts as Aabb{} (the origin)
+// and is united with each quad's padded box.  (The reference adds the z = min face twice and no z = max face;
+// the box of the list is the same either way.)
+Hittable createBox(Vec3 a, Vec3 b, const Material& mat) {
+    Hittable h;
+    h.type = RTB_HITTABLE_BOX;
+    h.a = a;
+    h.b = b;
+    h.mat = mat;
+    const Vec3 mn{std::fmin(a.x, b.x), std::fmin(a.y, b.y), std::fmin(a.z, b.z)};
+    const Vec3 mx{std::fmax(a.x, b.x), std::fmax(a.y, b.y), std::fmax(a.z, b.z)};
+    const Vec3 dx{mx.x - mn.x, 0, 0}, dy{0, mx.y - mn.y, 0}, dz{0, 0, mx.z - mn.z};
+    const Vec3 q[6] = {{mn.x, mn.y, mn.z}, {mx.x, mn.y, mx.z}, {mx.x, mn.y, mn.z},
+                       {mn.x, mn.y, mn.z}, {mn.x, mx.y, mx.z}, {mn.x, mn.y, mn.z}};
+    const Vec3 u[6] = {dx, -dz, -dx, dz, dx, dx};
+    const Vec3 v[6] = {dy, dy, dy, dy, -dz, dz};
+    Aabb box;  // Aabb{}: x = y = z = [0, 0]
+    for (int f = 0; f < 6; ++f) box = Aabb::fromBoxes(box, Aabb::fromPoints(q[f], q[f] + u[f] + v[f]).pad());
+    h.bounding_box = box;
+    return h;
+}
+
+Hittable RotateY::init(const Hittable& box, float angle_degrees) {  // objects.zig:354-397
+    Hittable h = box;
+    const float radians = angle_degrees * kPi / 180.0f;
+    h.sin_theta = std::sin(radians);
+    h.cos_theta = std::cos(radians);
+    h.rotated = true;
+    const Aabb& bbox = box.bounding_box;
+    const float inf = INFINITY;
+    float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            for (int k = 0; k < 2; ++k) {
+                const float i_f = (float)i, j_f = (float)j, k_f = (float)k;
+                const float x = i_f * bbox.x.max + (1 - i_f) * bbox.x.min;
+                const float y = j_f * bbox.y.max + (1 - j_f) * bbox.y.min;
+                const float z = k_f * bbox.z.max + (1 - k_f) * bbox.z.min;
+                const float newx = h.cos_theta * x + h.sin_theta * z;
+                const float newz = -h.sin_theta * x + h.cos_theta * z;
+                const float tester[3] = {newx, y, newz};
+                for (int c = 0; c < 3; ++c) {
+                    mn[c] = std::fmin(mn[c], tester[c]);
+                    mx[c] = std::fmax(mx[c], tester[c]);
+                }
+            }
+    h.bounding_box = Aabb::fromPoints({mn[0], mn[1], mn[2]}, {mx[0], mx[1], mx[2]});
+    return h;
+}
+
+Hittable Translate::init(const Hittable& box, Vec3 offset) {  // objects.zig:314-319, aabb.zig:51-57
+    Hittable h = box;
+    h.c = offset;
+    h.translated = true;
+    h.bounding_box.x = {box.bounding_box.x.min + offset.x, box.bounding_box.x.max + offset.x};
+    h.bounding_box.y = {box.bounding_box.y.min + offset.y, box.bounding_box.y.max + offset.y};
+    h.bounding_box.z = {box.bounding_box.z.min + offset.z, box.bounding_box.z.max + offset.z};
+    return h;
+}
+
 // ------------------------------------------------------------------ bvh.zig:43-103
 namespace {
 struct TreeBuilder {
@@ -335,6 +395,8 @@ std::unique_ptr<LoweredScene> World::lower() const {
         r.material = (uint32_t)ls->materials.size() - 1;
         r.is_moving = h.is_moving ? 1u : 0u;
         r.radius = h.radius;
+        r.sin_theta = h.sin_theta;
+        r.cos_theta = h.cos_theta;
         put3(r.a, h.a);
         put3(r.b, h.b);
         put3(r.c, h.c);
@@ -527,6 +589,29 @@ World twoPerlinWorld(HostRng& perlin_rng, HostRng& bvh_rng) {
     ObjectList objs;
     objs.push_back(Sphere::init({0, -1000, 0}, 1000, m));
     objs.push_back(Sphere::init({0, 2, 0}, 2, m));
+    return finishWorld(std::move(objs), bvh_rng, {});
+}
+
+World cornellBox(HostRng& bvh_rng) {  // main.zig:168-205; the camera half is cornell_camera() on the caller's side
+    const Material red = Lambertian::fromColor({0.65f, 0.05f, 0.05f});
+    const Material white = Lambertian::fromColor({0.73f, 0.73f, 0.73f});
+    const Material green = Lambertian::fromColor({0.12f, 0.45f, 0.15f});
+    const Material light = DiffuseLight::fromColor({15, 15, 15});
+    ObjectList objs;
+    objs.push_back(Quad::init({555, 0, 0}, {0, 555, 0}, {0, 0, 555}, green));
+    objs.push_back(Quad::init({0, 0, 0}, {0, 555, 0}, {0, 0, 555}, red));
+    objs.push_back(Quad::init({343, 554, 332}, {-130, 0, 0}, {0, 0, -105}, light));
+    objs.push_back(Quad::init({0, 0, 0}, {555, 0, 0}, {0, 0, 555}, white));
+    objs.push_back(Quad::init({555, 555, 555}, {-555, 0, 0}, {0, 0, -555}, white));
+    objs.push_back(Quad::init({0, 0, 555}, {555, 0, 0}, {0, 555, 0}, white));
+    Hittable box1 = createBox({0, 0, 0}, {165, 330, 165}, white);
+    box1 = RotateY::init(box1, 15);
+    box1 = Translate::init(box1, {265, 0, 295});
+    objs.push_back(box1);
+    Hittable box2 = createBox({0, 0, 0}, {165, 165, 165}, white);
+    box2 = RotateY::init(box2, -18);
+    box2 = Translate::init(box2, {130, 0, 65});
+    objs.push_back(box2);
     return finishWorld(std::move(objs), bvh_rng, {});
 }
 

@@ -122,11 +122,13 @@ struct DiffuseLight {
     static Material fromColor(Vec3 c);
 };
 
-struct Hittable {  // src/objects.zig:39-47 (sphere, quad)
+struct Hittable {  // src/objects.zig:39-47 (sphere, quad, and list/rotate_y/translate as used for boxes)
     uint32_t type = RTB_HITTABLE_SPHERE;
-    Vec3 a, b, c;  // sphere: center1, center_vec, -; quad: q, u, v
+    Vec3 a, b, c;  // sphere: center1, center_vec, -; quad: q, u, v; box: corner a, corner b, Translate.offset
     float radius = 0;
     bool is_moving = false;
+    float sin_theta = 0, cos_theta = 1;  // box: RotateY (identity until RotateY::init is applied)
+    bool rotated = false, translated = false;
     Material mat;
     Aabb bounding_box;
     const Aabb& boundingBox() const { return bounding_box; }
@@ -137,6 +139,17 @@ struct Sphere {
 };
 struct Quad {
     static Hittable init(Vec3 q, Vec3 u, Vec3 v, const Material& mat);
+};
+// createBox (src/objects.zig:510-532): a HittableList of six quads.  The reference wraps it as
+// Translate.init(RotateY.init(box, angle), offset) (src/main.zig:182-190); the three calls below compose the
+// same way on one flat object (RotateY must come before Translate, each at most once) and maintain the
+// bounding box exactly like HittableList.add / RotateY.init / Translate.init do.
+Hittable createBox(Vec3 a, Vec3 b, const Material& mat);
+struct RotateY {
+    static Hittable init(const Hittable& box, float angle_degrees);  // src/objects.zig:354-397
+};
+struct Translate {
+    static Hittable init(const Hittable& box, Vec3 offset);  // src/objects.zig:314-319
 };
 
 using ObjectList = std::vector<Hittable>;
@@ -222,6 +235,7 @@ World generateWorld(HostRng& scene_rng, HostRng& bvh_rng, const Book1Options& op
 World earthWorld(HostRng& bvh_rng, std::vector<Image> images);           // main.zig:88-99
 World twoSpheresWorld(HostRng& bvh_rng);                                 // main.zig:101-113
 World twoPerlinWorld(HostRng& perlin_rng, HostRng& bvh_rng);             // main.zig:115-125
+World cornellBox(HostRng& bvh_rng);                                      // main.zig:168-205 (objects only)
 World quadsWorld(HostRng& bvh_rng);                                      // main.zig:127-143
 World simpleLightWorld(HostRng& perlin_rng, HostRng& bvh_rng);           // main.zig:145-166
 // BASELINE config 3: the three textured worlds side by side in one BVH.

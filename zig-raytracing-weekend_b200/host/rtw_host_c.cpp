@@ -64,6 +64,9 @@ extern "C" int rtw_world_create(const RtwSceneParams* p, RtwWorld** out) {
         case RTW_SCENE_QUADS:
             w->world = quadsWorld(bvh_rng);
             break;
+        case RTW_SCENE_CORNELL_BOX:
+            w->world = cornellBox(bvh_rng);
+            break;
         case RTW_SCENE_SIMPLE_LIGHT:
             w->world = simpleLightWorld(perlin_rng, bvh_rng);
             break;
@@ -151,6 +154,19 @@ extern "C" int rtw_world_add_quad(RtwWorld* w, const float q[3], const float u[3
     const int rc = make_material(w, spec, &m);
     if (rc != RTB_OK) return rc;
     w->world.objects.push_back(Quad::init(V(q), V(u), V(v), m));
+    return RTB_OK;
+}
+
+extern "C" int rtw_world_add_box(RtwWorld* w, const float a[3], const float b[3], int rotate, float angle_degrees,
+                                 const float* offset_or_null, const RtwMaterialSpec* spec) {
+    if (!w || w->built || !a || !b) return RTB_ERR_INVALID_ARGUMENT;
+    Material m;
+    const int rc = make_material(w, spec, &m);
+    if (rc != RTB_OK) return rc;
+    Hittable box = createBox(V(a), V(b), m);
+    if (rotate) box = RotateY::init(box, angle_degrees);
+    if (offset_or_null) box = Translate::init(box, V(offset_or_null));
+    w->world.objects.push_back(box);
     return RTB_OK;
 }
 
