@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank renders --spp samples (sample partition only); strong: the ranks share "
+                         "--spp samples (samples) or the frame's tiles (tiles) — e.g. BASELINE config 5: "
+                         "--width 7680 --spp 1024 --scaling strong")
     ap.add_argument("--cpu-spp", type=int, default=0, help="samples per pixel of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -166,7 +170,8 @@ def run_reference(a):
 
 def workload_config(a, cam, integrator):
     return {"workload": f"book1 (generateWorld, ~485 spheres + BVH) {cam.image_width}x{cam.image_height}, "
-                        f"{a.spp} spp per GPU, depth {a.depth} [BASELINE configs[1]]",
+                        f"{a.spp} spp {'per GPU' if a.scaling == 'weak' and a.partition == 'samples' else 'in total'}, "
+                        f"depth {a.depth}" + (" [BASELINE configs[1]]" if (a.width, a.spp) == (WIDTH, SPP) else ""),
             "scene_seed": 1, "bvh_seed": 2, "render_seed": SEED, "integrator": integrator, "traversal": a.traversal,
             "partition": a.partition if a.gpus > 1 else "none", "background": "sky gradient (camera.zig:204-206)",
             "l2": "flushed between steps (256 MiB memset); scene is 47 KB and cache/smem resident by nature"}
@@ -213,7 +218,7 @@ def run_ours(a):
 
     def make_options(step, integrator, flags=0, spp=None, trav=None):
         part = mg.plan(a.partition, rank, world_size, spp or a.spp, sample_base=0,
-                       weak=(a.partition == "samples"))
+                       weak=(a.partition == "samples" and a.scaling == "weak"))
         o = p.render_options(seed=SEED + step, integrator=integrator, flags=flags,
                              traversal=traversal if trav is None else trav)
         return mg.apply(part, o), part
@@ -306,7 +311,7 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kernel_ms = t.tolist()
 
-    weak = a.partition == "samples"
+    weak = a.partition == "samples" and a.scaling == "weak"
     paths_per_step = npx * a.spp * (world_size if weak else 1)
     value = paths_per_step * a.steps / (total_ms * 1e-3) / 1e6
     # launches per step: one counting-free render reports them
@@ -327,7 +332,7 @@ def run_ours(a):
         step_device(0, vint, spp=vspp, trav=vtrav)
         e1.record(stream)
         torch.cuda.synchronize(dev)
-        variants[vname] = npx * vspp * (world_size if a.partition == "samples" else 1) / (e0.elapsed_time(e1) * 1e-3) / 1e6
+        variants[vname] = npx * vspp * (world_size if weak else 1) / (e0.elapsed_time(e1) * 1e-3) / 1e6
 
     # -- e2e: reference-facing call with HOST buffers (pinned), copies inside the timed region ------------------
     e2e = None
