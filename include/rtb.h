@@ -45,7 +45,7 @@ typedef enum RtbStatus {
 /* Hittable variants lowered from the tagged union at src/objects.zig:39-47.
  * LIST/TRANSLATE/ROTATE_Y/CONSTANT_MEDIUM are SURVEY §8(f) "next" rows; RoundBox is unfinished
  * in the reference (src/objects.zig:171-192) and has no tag. */
-enum { RTB_HITTABLE_SPHERE = 0, RTB_HITTABLE_QUAD = 1, RTB_HITTABLE_BOX = 2 };
+enum { RTB_HITTABLE_SPHERE = 0, RTB_HITTABLE_QUAD = 1, RTB_HITTABLE_BOX = 2, RTB_HITTABLE_CONSTANT_MEDIUM = 3 };
 
 /* Material variants, src/material.zig:11-16. */
 enum {
@@ -68,6 +68,12 @@ enum { RTB_TEX_SOLID = 0, RTB_TEX_CHECKER = 1, RTB_TEX_IMAGE = 2, RTB_TEX_NOISE 
  *            createBox (src/objects.zig:510-532, a HittableList of 6 quads), sin_theta / cos_theta =
  *            RotateY's fields (src/objects.zig:350-358; 0 / 1 when there is no RotateY), c =
  *            Translate.offset (src/objects.zig:309; zero when there is no Translate).
+ *   constant_medium (src/objects.zig:445-508) whose boundary is such a box, as in cornellBoxSmoke
+ *            (src/main.zig:223-236): the box fields as above, radius = neg_inv_density (-1/density, :451),
+ *            material = the Isotropic phase function (:451).  Its hit() draws one random number
+ *            (:484); that draw is word 0 of Philox block (0x40000000 + object index) of the ray
+ *            segment's stream, so it does not depend on the traversal order.  For rtb_trace_rays the
+ *            stream is keyed (seed 0; pixel = ray index, sample 0, segment 1).
  * The bounding box is not carried here: the BVH nodes hold the boxes the host computed
  * (Sphere.init / initMoving, src/objects.zig:80-92; RotateY.init :360-397; Translate.init :314-319). */
 typedef struct RtbHittable {

@@ -27,9 +27,10 @@ enum {
     RTW_SCENE_QUADS = 6,          /* quadsWorld          src/main.zig:127-143 */
     RTW_SCENE_SIMPLE_LIGHT = 7,   /* simpleLightWorld    src/main.zig:145-166 (camera: lookfrom (26,3,6), lookat
                                      (0,2,0), depth 50, defocus 0, black background) */
-    RTW_SCENE_CORNELL_BOX = 8     /* cornellBox          src/main.zig:168-205 — HEAD's selected scene (:422);
+    RTW_SCENE_CORNELL_BOX = 8,    /* cornellBox          src/main.zig:168-205 — HEAD's selected scene (:422);
                                      camera: 600 x 600, 200 spp, depth 200, vfov 40, lookfrom (278,278,-800),
                                      lookat (278,278,0), defocus 0, black background */
+    RTW_SCENE_CORNELL_SMOKE = 9   /* cornellBoxSmoke     src/main.zig:207-251 (same camera, depth 50) */
 };
 enum {
     RTW_BOOK1_CHECKER_GROUND = 1u << 0, /* HEAD's checker ground (main.zig:257-260) instead of Book-1 grey */
@@ -76,6 +77,10 @@ int rtw_world_add_quad(RtwWorld* world, const float q[3], const float u[3], cons
  * rotate = 0 skips RotateY, offset = NULL skips Translate (src/objects.zig:314-319, :354-397, :510-532). */
 int rtw_world_add_box(RtwWorld* world, const float a[3], const float b[3], int rotate, float angle_degrees,
                       const float* offset_or_null, const RtwMaterialSpec* material);
+/* ConstantMedium.initFromColor(&box, density, color) with the same kind of box as the boundary
+ * (src/objects.zig:450-452; cornellBoxSmoke src/main.zig:223-236). */
+int rtw_world_add_medium(RtwWorld* world, const float a[3], const float b[3], int rotate, float angle_degrees,
+                         const float* offset_or_null, float density, const float color[3]);
 int rtw_world_build(RtwWorld* world, uint64_t bvh_seed); /* BVHTree.init + lowering */
 
 const RtbSceneDesc* rtw_world_desc(const RtwWorld* world); /* valid until rtw_world_destroy */

@@ -257,6 +257,38 @@ bool quadHitQUV(V3 q, V3 u, V3 v, uint32_t material, const Ray& r, Interval ray_
 }
 
 // Hittable.hit dispatch, objects.zig:49-53
+// The RNG stream of the ray segment being traced: ConstantMedium.hit draws a random number INSIDE hit
+// (objects.zig:484).  Its draw is word 0 of block (0x40000000 + object index) of the segment's stream, so it
+// does not depend on the order in which the tree is walked.  Set by the callers of worldHit.
+struct HitCtx {
+    uint64_t seed = 0;
+    uint32_t pixel = 0, sample = 0, segment = 1;
+};
+thread_local HitCtx g_ctx;
+
+// ConstantMedium.hit (objects.zig:462-507) with a box instance as the boundary (cornellBoxSmoke, main.zig:223-236).
+bool mediumHit(const RtbHittable& m, uint32_t index, const Ray& r, Interval ray_t, HitRecord& rec) {
+    HitRecord rec_1, rec_2;
+    if (!boxHit(m, r, Interval{-kInfinity, kInfinity}, rec_1)) return false;               // intervals.universe
+    if (!boxHit(m, r, Interval{rec_1.t + 0.0001f, kInfinity}, rec_2)) return false;
+    if (rec_1.t < ray_t.min) rec_1.t = ray_t.min;
+    if (rec_2.t > ray_t.max) rec_2.t = ray_t.max;
+    if (rec_1.t >= rec_2.t) return false;
+    if (rec_1.t < 0) rec_1.t = 0;
+    const float ray_length = length(r.direction);
+    const float distance_inside_boundary = (rec_2.t - rec_1.t) * ray_length;
+    const float rnd = rng_block(g_ctx.seed, g_ctx.pixel, g_ctx.sample, g_ctx.segment, 0x40000000u + index).r[0];
+    const float hit_distance = m.radius * std::log(rnd);  // radius carries neg_inv_density = -1/d (objects.zig:451)
+    if (hit_distance > distance_inside_boundary) return false;
+    rec = HitRecord{};
+    rec.t = rec_1.t + hit_distance / ray_length;
+    rec.p = at(r, rec.t);
+    rec.normal = v3(1, 0, 0);  // arbitrary
+    rec.front_face = true;     // also arbitrary
+    rec.mat = m.material;      // phase_function (Isotropic)
+    return true;
+}
+
 bool hittableHit(const RtbSceneDesc* sc, uint32_t index, const Ray& r, Interval ray_t, HitRecord& rec) {
     const RtbHittable& h = sc->hittables[index];
     bool ok = false;
@@ -266,6 +298,8 @@ bool hittableHit(const RtbSceneDesc* sc, uint32_t index, const Ray& r, Interval 
         ok = quadHit(h, r, ray_t, rec);
     else if (h.type == RTB_HITTABLE_BOX)
         ok = boxHit(h, r, ray_t, rec);
+    else if (h.type == RTB_HITTABLE_CONSTANT_MEDIUM)
+        ok = mediumHit(h, index, r, ray_t, rec);
     if (ok) rec.object = (int32_t)index;
     return ok;
 }
@@ -516,6 +550,7 @@ V3 rayColor(const RtbSceneDesc* sc, const RtbCamera* cam, const Ray& r, uint32_t
     const Interval ray_t{0.001f, kInfinity};
     ++cn.rays;
     HitRecord rec;
+    g_ctx = HitCtx{seed, pixel, sample, segment};
     if (worldHit(sc, r, ray_t, rec, cn)) {
         ++cn.hits;
         Ray scattered{v3(0, 0, 0), v3(0, 0, 0), 0};
@@ -687,6 +722,7 @@ int orc_hittable_hit(const RtbSceneDesc* scene, uint32_t index, const RtbRay* ra
     HitRecord rec;
     Counters cn;
     cn.obj = 1;
+    g_ctx = HitCtx{};
     const bool ok = hittableHit(scene, index, toRay(ray), Interval{ray->t_min, ray->t_max}, rec);
     fillHit(rec, ok, cn, hit);
     return ok ? 1 : 0;
@@ -696,6 +732,7 @@ void orc_trace_rays(const RtbSceneDesc* scene, const RtbRay* rays, uint64_t n, R
     for (uint64_t i = 0; i < n; ++i) {
         HitRecord rec;
         Counters cn;
+        g_ctx = HitCtx{0, (uint32_t)i, 0, 1};  // ray queries: medium draws are keyed (seed 0; pixel = ray index)
         const bool ok = worldHit(scene, toRay(&rays[i]), Interval{rays[i].t_min, rays[i].t_max}, rec, cn);
         fillHit(rec, ok, cn, &hits_out[i]);
     }

@@ -152,6 +152,13 @@ class World:
         _check(_ffi.rtw().rtw_world_add_box(self._h, C.byref(_vec3(a)), C.byref(_vec3(b)), int(angle is not None),
                                             float(angle or 0.0), off, C.byref(spec)), "rtw_world_add_box")
 
+    def add_medium(self, a, b, density, color, angle=None, offset=None):
+        """ConstantMedium.initFromColor(&Translate(RotateY(createBox(a, b))), density, color)."""
+        off = C.byref(_vec3(offset)) if offset is not None else None
+        _check(_ffi.rtw().rtw_world_add_medium(self._h, C.byref(_vec3(a)), C.byref(_vec3(b)), int(angle is not None),
+                                               float(angle or 0.0), off, float(density), C.byref(_vec3(color))),
+               "rtw_world_add_medium")
+
     def build(self, bvh_seed=2):
         _check(_ffi.rtw().rtw_world_build(self._h, bvh_seed), "rtw_world_build")
         return self

@@ -24,7 +24,7 @@ RTB_ERR_OUT_OF_MEMORY = -4
 RTB_ERR_CANCELLED = -5
 RTB_ERR_UNSUPPORTED = -6
 
-RTB_HITTABLE_SPHERE, RTB_HITTABLE_QUAD, RTB_HITTABLE_BOX = 0, 1, 2
+RTB_HITTABLE_SPHERE, RTB_HITTABLE_QUAD, RTB_HITTABLE_BOX, RTB_HITTABLE_CONSTANT_MEDIUM = 0, 1, 2, 3
 RTB_MAT_LAMBERTIAN, RTB_MAT_METAL, RTB_MAT_DIELECTRIC, RTB_MAT_DIFFUSE_LIGHT, RTB_MAT_ISOTROPIC = range(5)
 RTB_TEX_SOLID, RTB_TEX_CHECKER, RTB_TEX_IMAGE, RTB_TEX_NOISE = range(4)
 RTB_BACKGROUND_SOLID, RTB_BACKGROUND_SKY = 0, 1
@@ -33,7 +33,7 @@ RTB_TRAVERSAL_REFERENCE, RTB_TRAVERSAL_ORDERED, RTB_TRAVERSAL_SAH = 0, 1, 2
 RTB_FLAG_COUNT_WORK = 1
 
 RTW_SCENE_BOOK1, RTW_SCENE_EARTH, RTW_SCENE_TWO_SPHERES, RTW_SCENE_TWO_PERLIN, RTW_SCENE_TEXTURED, \
-    RTW_SCENE_RANDOM_SPHERES, RTW_SCENE_QUADS, RTW_SCENE_SIMPLE_LIGHT, RTW_SCENE_CORNELL_BOX = range(9)
+    RTW_SCENE_RANDOM_SPHERES, RTW_SCENE_QUADS, RTW_SCENE_SIMPLE_LIGHT, RTW_SCENE_CORNELL_BOX, RTW_SCENE_CORNELL_SMOKE = range(10)
 RTW_BOOK1_CHECKER_GROUND, RTW_BOOK1_EARTH_SPHERE, RTW_BOOK1_STATIC_SPHERES = 1, 2, 4
 
 f32, u32, i32, u64, u16, u8 = C.c_float, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint16, C.c_uint8
@@ -134,7 +134,7 @@ RTB_SYMBOLS = [
 ]
 RTW_SYMBOLS = [
     "rtw_world_create", "rtw_world_new", "rtw_world_add_image", "rtw_world_add_sphere", "rtw_world_add_quad",
-    "rtw_world_add_box",
+    "rtw_world_add_box", "rtw_world_add_medium",
     "rtw_world_build", "rtw_world_desc", "rtw_world_object_box", "rtw_world_destroy", "rtw_camera_defaults",
     "rtw_camera_init", "rtw_camera_render", "rtw_write_ppm",
 ]
@@ -203,6 +203,8 @@ def rtw() -> C.CDLL:
                                        C.POINTER(RtwMaterialSpec)]
     lib.rtw_world_add_box.argtypes = [vp, C.POINTER(f32 * 3), C.POINTER(f32 * 3), C.c_int, f32, C.POINTER(f32 * 3),
                                       C.POINTER(RtwMaterialSpec)]
+    lib.rtw_world_add_medium.argtypes = [vp, C.POINTER(f32 * 3), C.POINTER(f32 * 3), C.c_int, f32, C.POINTER(f32 * 3),
+                                         f32, C.POINTER(f32 * 3)]
     lib.rtw_world_build.argtypes = [vp, u64]
     lib.rtw_world_desc.argtypes = [vp]
     lib.rtw_world_desc.restype = C.POINTER(RtbSceneDesc)

@@ -124,7 +124,7 @@ static uint32_t append_complex(std::vector<DevQuad>& table, const RtbHittable& h
     }
     DevQuad hdr{};
     hdr.q_d = make_float4(h.c[0], h.c[1], h.c[2], h.sin_theta);
-    hdr.u = make_float4(h.cos_theta, 0.0f, 0.0f, 0.0f);
+    hdr.u = make_float4(h.cos_theta, h.type == RTB_HITTABLE_CONSTANT_MEDIUM ? h.radius : 0.0f, 0.0f, 0.0f);  // u.y = neg_inv_density
     table.push_back(hdr);
     const float mn[3] = {std::fmin(h.a[0], h.b[0]), std::fmin(h.a[1], h.b[1]), std::fmin(h.a[2], h.b[2])};
     const float mx[3] = {std::fmax(h.a[0], h.b[0]), std::fmax(h.a[1], h.b[1]), std::fmax(h.a[2], h.b[2])};
@@ -165,7 +165,7 @@ static int validate_desc(const RtbSceneDesc* d) {
         return fail(RTB_ERR_INVALID_ARGUMENT, "root %d out of range", d->root);
     for (uint32_t i = 0; i < d->n_hittables; ++i) {
         const RtbHittable& h = d->hittables[i];
-        if (h.type != RTB_HITTABLE_SPHERE && h.type != RTB_HITTABLE_QUAD && h.type != RTB_HITTABLE_BOX)
+        if (h.type > RTB_HITTABLE_CONSTANT_MEDIUM)
             return fail(RTB_ERR_UNSUPPORTED, "hittable %u: unsupported type %u", i, h.type);
         if (h.material >= d->n_materials) return fail(RTB_ERR_INVALID_ARGUMENT, "hittable %u: material out of range", i);
     }
@@ -245,7 +245,9 @@ static void leaf_record(const RtbSceneDesc* d, uint32_t object, const std::vecto
         *f1 = mkf4(h.b[0], h.b[1], h.b[2], h.radius);
     } else {
         *f0 = mkf4(0, 0, 0, bits((KIND_QUAD << 30) | object));
-        *f1 = mkf4(bits(h.type == RTB_HITTABLE_BOX ? COMPLEX_BOX : COMPLEX_QUAD), 0, 0, bits(quad_slot[object]));
+        const uint32_t subtype = h.type == RTB_HITTABLE_BOX ? COMPLEX_BOX
+                                 : h.type == RTB_HITTABLE_CONSTANT_MEDIUM ? COMPLEX_MEDIUM : COMPLEX_QUAD;
+        *f1 = mkf4(bits(subtype), 0, 0, bits(quad_slot[object]));
     }
 }
 

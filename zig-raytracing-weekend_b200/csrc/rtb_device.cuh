@@ -260,7 +260,7 @@ __device__ __forceinline__ bool slab_miss(float4 f0, float4 f1, float3 o, float 
 // A box instance = Translate(RotateY(createBox(a, b, mat), angle), offset) (src/objects.zig:308-443, :510-532),
 // stored in the quad table as a header entry {q_d = (offset.xyz, sin_theta), u.x = cos_theta} followed by
 // the 6 quads createBox makes, in its order.  Leaf record of a complex object: f1.x = bits(subtype).
-enum : uint32_t { COMPLEX_QUAD = 0u, COMPLEX_BOX = 1u };
+enum : uint32_t { COMPLEX_QUAD = 0u, COMPLEX_BOX = 1u, COMPLEX_MEDIUM = 2u };
 
 // Translate.hit (:331-335) then RotateY.hit (:410-421): the ray in the box's own frame.
 __device__ __forceinline__ DRay box_local_ray(const DRay& r, const DevQuad& hdr) {
@@ -296,15 +296,40 @@ __device__ __forceinline__ bool box_root(const DRay& r, const DevQuad* __restric
     return hit;
 }
 
-// Leaf test of a complex object (quad or box instance); f1 = {bits(subtype), -, -, bits(table slot)}.
+// ConstantMedium.hit (src/objects.zig:462-507) with a box instance as the boundary; the table entry is a box
+// whose header carries neg_inv_density in u.y.  The one random number it draws (:484) is word 0 of block
+// (0x40000000 + object) of the segment's stream — independent of the order in which the tree is walked.
+__device__ __forceinline__ bool medium_root(const DRay& r, const DevQuad* __restrict__ entry, float t_min, float t_max,
+                                            const RngKey& key, uint32_t segment, uint32_t object, float& t_out) {
+    const float inf = __int_as_float(0x7f800000);
+    float t1, t2, alpha, beta;
+    uint32_t face;
+    if (!box_root(r, entry, -inf, inf, t1, face, alpha, beta)) return false;          // intervals.universe
+    if (!box_root(r, entry, t1 + 0.0001f, inf, t2, face, alpha, beta)) return false;
+    if (t1 < t_min) t1 = t_min;
+    if (t2 > t_max) t2 = t_max;
+    if (t1 >= t2) return false;
+    if (t1 < 0.0f) t1 = 0.0f;
+    const float ray_length = sqrtf(length_squared(r.d));
+    const float distance_inside_boundary = (t2 - t1) * ray_length;
+    const float hit_distance = entry[0].u.y * logf(rng_block(key, segment, 0x40000000u + object).x);
+    if (hit_distance > distance_inside_boundary) return false;
+    t_out = t1 + hit_distance / ray_length;
+    return true;
+}
+
+// Leaf test of a complex object (quad, box instance or constant medium); f1 = {bits(subtype), -, -, bits(slot)}.
 __device__ __forceinline__ bool complex_root(const DRay& r, const DevQuad* __restrict__ quads, float4 f1, float t_min,
-                                             float t_max, float& t_out) {
+                                             float t_max, float& t_out, const RngKey& key, uint32_t segment,
+                                             uint32_t object) {
     const DevQuad* __restrict__ entry = quads + __float_as_uint(f1.w);
+    const uint32_t subtype = __float_as_uint(f1.x);
     float alpha, beta;
-    if (__float_as_uint(f1.x) == COMPLEX_BOX) {
+    if (subtype == COMPLEX_BOX) {
         uint32_t face;
         return box_root(r, entry, t_min, t_max, t_out, face, alpha, beta);
     }
+    if (subtype == COMPLEX_MEDIUM) return medium_root(r, entry, t_min, t_max, key, segment, object, t_out);
     return quad_root(r, entry[0], t_min, t_max, t_out, alpha, beta);
 }
 
@@ -360,7 +385,8 @@ template <bool COUNT, bool QUADS, bool SMEM>
 __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ nodes, const DevQuad* __restrict__ quads,
                                                    float3 o, float3 d, float time, float inv_x, float inv_y,
                                                    float inv_z, float t_min, float t_max, uint32_t& n_box,
-                                                   uint32_t& n_obj, uint32_t smem_base = 0u) {
+                                                   uint32_t& n_obj, uint32_t smem_base = 0u, RngKey key = RngKey{},
+                                                   uint32_t segment = 1u) {
     // smem_base (SMEM only): 32-bit shared-window address of the staged layout.  The caller adds a
     // run-time zero to it so that ptxas keeps it in a register instead of rematerialising the window
     // base (S2UR/UMOV/UIADD3/ULEA) in every iteration of the node loop.
@@ -405,7 +431,7 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
                 r.d = d;
                 r.time = time;
                 float t;
-                if (complex_root(r, quads, f1, t_min, best.t, t)) {
+                if (complex_root(r, quads, f1, t_min, best.t, t, key, segment, meta & RTB_META_INDEX_MASK)) {
                     best.t = t;
                     best.node = meta & RTB_META_INDEX_MASK;
                 }
@@ -427,7 +453,8 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
 template <bool COUNT, bool QUADS>
 __device__ __forceinline__ Nearest traverse_reference(const float4* __restrict__ nodes, uint32_t n_nodes,
                                                       const DevQuad* __restrict__ quads, const DRay& r, float t_min,
-                                                      float t_max, uint32_t& n_box, uint32_t& n_obj) {
+                                                      float t_max, uint32_t& n_box, uint32_t& n_obj,
+                                                      RngKey key = RngKey{}, uint32_t segment = 1u) {
     Nearest best;
     best.t = t_max;
     best.node = 0xffffffffu;
@@ -453,7 +480,7 @@ __device__ __forceinline__ Nearest traverse_reference(const float4* __restrict__
                 }
             } else {
                 float t;
-                if (complex_root(r, quads, f1, t_min, best.t, t)) {
+                if (complex_root(r, quads, f1, t_min, best.t, t, key, segment, meta & RTB_META_INDEX_MASK)) {
                     best.t = t;
                     best.node = i;
                 }
@@ -500,6 +527,10 @@ __device__ __forceinline__ DHit finish_hit_rec(float4 f0, float4 f1, const DevQu
         const float3 center = (kind == KIND_MOVING_SPHERE) ? c1 + splat3(r.time) * f3(f1) : c1;
         outward = (h.p - center) / splat3(f1.w);
         if (WANT_UV) sphere_uv(outward, h.u, h.v);
+    } else if (__float_as_uint(f1.x) == COMPLEX_MEDIUM) {
+        h.normal = f3(1.0f, 0.0f, 0.0f);  // "arbitrary" (src/objects.zig:493-494)
+        h.front_face = true;
+        return h;
     } else if (__float_as_uint(f1.x) == COMPLEX_BOX) {
         // Re-run the list test to learn which face was hit (same arithmetic, same t), build the record in the
         // box's frame (Quad.hit :250-260), then rotate back (RotateY.hit :425-439) and translate (:338-342).

@@ -58,10 +58,11 @@ __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderPar
                     const float4* oct =
                         P.scene.oct_nodes[P.ordered] + (size_t)ray_octant(ix, iy, iz) * 2u * (P.scene.n_nodes + 1u);
                     best = traverse_octant<COUNT, QUADS, false>(oct, P.scene.quads, ray.o, ray.d, ray.time, ix, iy, iz,
-                                                                0.001f, __int_as_float(0x7f800000), n_box, n_obj);
+                                                                0.001f, __int_as_float(0x7f800000), n_box, n_obj, 0u,
+                                                                key, segment);
                 } else {
                     best = traverse_reference<COUNT, QUADS>(nodes, P.scene.n_nodes, P.scene.quads, ray, 0.001f,
-                                                            __int_as_float(0x7f800000), n_box, n_obj);
+                                                            __int_as_float(0x7f800000), n_box, n_obj, key, segment);
                 }
                 bool done;
                 if (best.node == 0xffffffffu) {
@@ -174,15 +175,20 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     r.d = f3(rr.direction[0], rr.direction[1], rr.direction[2]);
     r.time = rr.time;
     uint32_t n_box = 0, n_obj = 0;
+    // ray queries key the constant-medium draw by the ray index (seed 0, sample 0, segment 1), see rtb.h
+    RngKey qkey;
+    qkey.seed = make_uint2(0u, 0u);
+    qkey.pixel = (uint32_t)i;
+    qkey.sample = 0u;
     Nearest best;
     if (ORDERED) {
         const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
         const float4* oct = scene.oct_nodes[layout] + (size_t)ray_octant(ix, iy, iz) * 2u * (scene.n_nodes + 1u);
         best = traverse_octant<true, QUADS, false>(oct, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min, rr.t_max,
-                                                   n_box, n_obj);
+                                                   n_box, n_obj, 0u, qkey, 1u);
     } else {
         best = traverse_reference<true, QUADS>(scene.nodes, scene.n_nodes, scene.quads, r, rr.t_min, rr.t_max, n_box,
-                                               n_obj);
+                                               n_obj, qkey, 1u);
     }
     RtbHit h;
     h.object = -1;

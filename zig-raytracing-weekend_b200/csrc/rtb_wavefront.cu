@@ -201,9 +201,16 @@ __global__ void __launch_bounds__(256) wf_extend(const WfParams P) {
             const float4 b = P.in.rays[2u * at + 1u];
             const float3 o = f3(a), d = f3(b);
             if (COUNT) ++n_rays;
+            RngKey key = RngKey{};
+            if (QUADS) {  // only complex objects (constant media) draw random numbers inside hit()
+                const uint32_t slot = __float_as_uint(b.w);
+                key.seed = P.R.seed;
+                slot_pixel(P.R, slot % P.slots_per_sample, key.pixel);
+                key.sample = P.batch_begin + slot / P.slots_per_sample;
+            }
             const Nearest best = traverse_octant<COUNT, QUADS, SMEM_NODES>(
                 nodes, P.R.scene.quads, o, d, a.w, 1.0f / d.x, 1.0f / d.y, 1.0f / d.z, 0.001f, __int_as_float(0x7f800000),
-                n_box, n_obj, smem_base);
+                n_box, n_obj, smem_base, key, P.segment);
             if (best.node != 0xffffffffu) cls = P.R.scene.object_class[best.node];
             entry = make_uint4((uint32_t)at, __float_as_uint(best.t), best.node, 0u);
         }

@@ -262,6 +262,22 @@ Hittable Translate::init(const Hittable& box, Vec3 offset) {  // objects.zig:314
     return h;
 }
 
+Material Isotropic::init(const Texture& t) {
+    Material m;
+    m.type = RTB_MAT_ISOTROPIC;
+    m.texture = t;
+    return m;
+}
+Material Isotropic::fromColor(Vec3 c) { return init(SolidColor::init(c)); }
+
+Hittable ConstantMedium::initFromColor(const Hittable& boundary, float d, Vec3 c) {  // objects.zig:450-452
+    Hittable h = boundary;  // keeps the box fields and the boundary's bounding box (:458-460)
+    h.type = RTB_HITTABLE_CONSTANT_MEDIUM;
+    h.radius = -1.0f / d;   // neg_inv_density
+    h.mat = Isotropic::fromColor(c);
+    return h;
+}
+
 // ------------------------------------------------------------------ bvh.zig:43-103
 namespace {
 struct TreeBuilder {
@@ -612,6 +628,29 @@ World cornellBox(HostRng& bvh_rng) {  // main.zig:168-205; the camera half is co
     box2 = RotateY::init(box2, -18);
     box2 = Translate::init(box2, {130, 0, 65});
     objs.push_back(box2);
+    return finishWorld(std::move(objs), bvh_rng, {});
+}
+
+World cornellBoxSmoke(HostRng& bvh_rng) {  // main.zig:207-251
+    const Material red = Lambertian::fromColor({0.65f, 0.05f, 0.05f});
+    const Material white = Lambertian::fromColor({0.73f, 0.73f, 0.73f});
+    const Material green = Lambertian::fromColor({0.12f, 0.45f, 0.15f});
+    const Material light = DiffuseLight::fromColor({7, 7, 7});
+    ObjectList objs;
+    objs.push_back(Quad::init({555, 0, 0}, {0, 555, 0}, {0, 0, 555}, green));
+    objs.push_back(Quad::init({0, 0, 0}, {0, 555, 0}, {0, 0, 555}, red));
+    objs.push_back(Quad::init({113, 554, 127}, {330, 0, 0}, {0, 0, 305}, light));
+    objs.push_back(Quad::init({0, 0, 0}, {555, 0, 0}, {0, 0, 555}, white));
+    objs.push_back(Quad::init({555, 555, 555}, {-555, 0, 0}, {0, 0, -555}, white));
+    objs.push_back(Quad::init({0, 0, 555}, {555, 0, 0}, {0, 555, 0}, white));
+    Hittable box1 = createBox({0, 0, 0}, {165, 330, 165}, white);
+    box1 = RotateY::init(box1, 15);
+    box1 = Translate::init(box1, {265, 0, 295});
+    objs.push_back(ConstantMedium::initFromColor(box1, 0.01f, {0, 0, 0}));
+    Hittable box2 = createBox({0, 0, 0}, {165, 165, 165}, white);
+    box2 = RotateY::init(box2, -18);
+    box2 = Translate::init(box2, {130, 0, 65});
+    objs.push_back(ConstantMedium::initFromColor(box2, 0.01f, {1, 1, 1}));
     return finishWorld(std::move(objs), bvh_rng, {});
 }
 

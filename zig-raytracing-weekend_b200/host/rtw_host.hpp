@@ -151,6 +151,15 @@ struct RotateY {
 struct Translate {
     static Hittable init(const Hittable& box, Vec3 offset);  // src/objects.zig:314-319
 };
+struct Isotropic {
+    static Material init(const Texture& t);  // src/material.zig:131-133
+    static Material fromColor(Vec3 c);       // src/material.zig:135-137
+};
+struct ConstantMedium {
+    // src/objects.zig:450-452: boundary (a box instance here, as in cornellBoxSmoke), neg_inv_density = -1/d,
+    // phase_function = Isotropic(SolidColor(c)); boundingBox() = the boundary's (:458-460).
+    static Hittable initFromColor(const Hittable& boundary, float d, Vec3 c);
+};
 
 using ObjectList = std::vector<Hittable>;
 
@@ -236,6 +245,7 @@ World earthWorld(HostRng& bvh_rng, std::vector<Image> images);           // main
 World twoSpheresWorld(HostRng& bvh_rng);                                 // main.zig:101-113
 World twoPerlinWorld(HostRng& perlin_rng, HostRng& bvh_rng);             // main.zig:115-125
 World cornellBox(HostRng& bvh_rng);                                      // main.zig:168-205 (objects only)
+World cornellBoxSmoke(HostRng& bvh_rng);                                 // main.zig:207-251 (objects only)
 World quadsWorld(HostRng& bvh_rng);                                      // main.zig:127-143
 World simpleLightWorld(HostRng& perlin_rng, HostRng& bvh_rng);           // main.zig:145-166
 // BASELINE config 3: the three textured worlds side by side in one BVH.

@@ -67,6 +67,9 @@ extern "C" int rtw_world_create(const RtwSceneParams* p, RtwWorld** out) {
         case RTW_SCENE_CORNELL_BOX:
             w->world = cornellBox(bvh_rng);
             break;
+        case RTW_SCENE_CORNELL_SMOKE:
+            w->world = cornellBoxSmoke(bvh_rng);
+            break;
         case RTW_SCENE_SIMPLE_LIGHT:
             w->world = simpleLightWorld(perlin_rng, bvh_rng);
             break;
@@ -167,6 +170,16 @@ extern "C" int rtw_world_add_box(RtwWorld* w, const float a[3], const float b[3]
     if (rotate) box = RotateY::init(box, angle_degrees);
     if (offset_or_null) box = Translate::init(box, V(offset_or_null));
     w->world.objects.push_back(box);
+    return RTB_OK;
+}
+
+extern "C" int rtw_world_add_medium(RtwWorld* w, const float a[3], const float b[3], int rotate, float angle_degrees,
+                                    const float* offset_or_null, float density, const float color[3]) {
+    if (!w || w->built || !a || !b || !color || !(density > 0)) return RTB_ERR_INVALID_ARGUMENT;
+    Hittable box = createBox(V(a), V(b), Lambertian::fromColor({0.73f, 0.73f, 0.73f}));  // boundary material is unused
+    if (rotate) box = RotateY::init(box, angle_degrees);
+    if (offset_or_null) box = Translate::init(box, V(offset_or_null));
+    w->world.objects.push_back(ConstantMedium::initFromColor(box, density, V(color)));
     return RTB_OK;
 }
 
