@@ -26,14 +26,28 @@ def test_layout_invariants(pkg, scene, earthmap):
     for mode in (0, 1, 2):
         for octant in range(8):
             L, n = _layout(pkg, world, mode, octant)
-            assert n == d.n_nodes
+            # modes 0/1: the host's 2k-1 nodes; mode 2 (SAH) puts a box node in front of each of the k leaves
+            assert n == (d.n_nodes if mode < 2 else d.n_nodes + (d.n_nodes + 1) // 2)
             meta = L[:, 3].view(np.uint32)
             assert meta[n] == END                                       # the sentinel closes every octant
             kind, idx = meta[:n] >> 30, meta[:n] & 0x3FFFFFFF
             leaves = kind != 0
             assert sorted(idx[leaves].tolist()) == list(range(d.n_hittables))   # every object exactly once
             inner = np.nonzero(~leaves)[0]
-            assert (idx[inner] > inner + 2).all() and (idx[inner] <= n).all()   # skip jumps over >= 2 children
+            if mode < 2:
+                assert (idx[inner] > inner + 2).all() and (idx[inner] <= n).all()   # skip jumps over >= 2 children
+            else:
+                leaf_box = inner[idx[inner] == inner + 2]          # {object box, skip past the leaf}, {leaf}
+                assert leaves[leaf_box + 1].all() and len(leaf_box) == d.n_hittables
+                assert (idx[inner] >= inner + 2).all() and (idx[inner] <= n).all()
+                # the leaf's box is the host's box for that object, padded outwards by <= 2^-20 of the scene extent
+                obj = idx[leaf_box + 1]
+                host = np.array([world.object_box(int(k)) for k in obj], np.float32)
+                lo = np.minimum(L[leaf_box, :3], L[leaf_box, 4:7])
+                hi = np.maximum(L[leaf_box, :3], L[leaf_box, 4:7])
+                extent = np.abs(host).reshape(-1, 2, 3).max(axis=(0, 1))
+                assert (lo <= host[:, :3]).all() and (hi >= host[:, 3:]).all()
+                assert (host[:, :3] - lo <= extent * 2.0 ** -20).all() and (hi - host[:, 3:] <= extent * 2.0 ** -20).all()
             # pre-swapped slabs: entry plane = max where the octant bit is set, min otherwise
             for a in range(3):
                 lo, hi = L[inner, a], L[inner, 4 + a]
@@ -60,7 +74,7 @@ def _walk(L, n, hittables, ray):
         best_t, best_obj = f(np.inf), -1
         tmin = f(0.001)
         a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
-        i, n_box = 0, 0
+        i, n_box, n_obj = 0, 0, 0
         meta = L[:, 3].view(np.uint32)
         while True:
             m = int(meta[i])
@@ -75,6 +89,7 @@ def _walk(L, n, hittables, ray):
             if m == END:
                 break
             kind, obj = m >> 30, m & 0x3FFFFFFF
+            n_obj += 1
             if kind != 3:
                 c = L[i, :3] + (time * L[i, 4:7] if kind == 2 else f(0))
                 oc = o - c
@@ -89,7 +104,7 @@ def _walk(L, n, hittables, ray):
                     if tmin < root < best_t:
                         best_t, best_obj = root, obj
             i += 1
-    return best_obj, best_t, n_box
+    return best_obj, best_t, n_box, n_obj
 
 
 def test_python_walk_of_every_layout_finds_the_oracle_hits(pkg, orc):
@@ -108,17 +123,20 @@ def test_python_walk_of_every_layout_finds_the_oracle_hits(pkg, orc):
     cpu = orc.trace_rays(world.desc, rays)
     layouts = {(m, o): _layout(pkg, world, m, o) for m in (0, 1, 2) for o in range(8)}
     total = {0: 0, 1: 0, 2: 0}
+    total_obj = {0: 0, 1: 0, 2: 0}
     for k, ray in enumerate(rays):
         with np.errstate(divide="ignore"):
             inv = np.float32(1) / ray["direction"]
         octant = int(inv[0] < 0) | (int(inv[1] < 0) << 1) | (int(inv[2] < 0) << 2)
         for mode in (0, 1, 2):
             L, n = layouts[(mode, octant)]
-            obj, t, n_box = _walk(L, n, d.hittables, ray)
+            obj, t, n_box, n_obj = _walk(L, n, d.hittables, ray)
             assert obj == cpu["object"][k], (k, mode)
             if obj >= 0:
                 assert np.float32(t) == cpu["t"][k]
             if mode == 0:
                 assert n_box == cpu["n_box_tests"][k]      # reference order: the very same node visits
             total[mode] += n_box
-    assert total[1] <= total[0] and total[2] < 0.6 * total[0]   # SAH re-partition: far fewer slab tests
+            total_obj[mode] += n_obj
+    # SAH re-partition with box-tested leaves: far fewer slab tests and far fewer primitive tests
+    assert total[1] <= total[0] and total[2] < 0.65 * total[0] and total_obj[2] < 0.35 * total_obj[0]

@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "_lib")
+# RTB_LIB_DIR: development knob (tools/ experiments with variant builds, see the Makefile); unset everywhere else.
+LIB_DIR = os.environ.get("RTB_LIB_DIR") or os.path.join(_HERE, "_lib")
 
 RTB_ABI_VERSION = 1
 

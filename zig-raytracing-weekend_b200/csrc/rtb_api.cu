@@ -255,8 +255,13 @@ static void leaf_record(const RtbSceneDesc* d, uint32_t object, const std::vecto
 // octant 0..7: bounds pre-swapped to (entry, exit) planes for rays with invD<0 on the axes whose bit
 // is set; child order = reference (left first) or, if `ordered`, the child the ray meets first along
 // the axis that separates the two children most (the builder split on box-min order, bvh.zig:64-67).
+// box_leaves: every leaf is preceded by a box node holding the leaf's own bounds (skip = past the leaf), so the
+// primitive test only runs for rays that enter the object's box; a subtree of s nodes then takes s + (s+1)/2 slots.
+static inline uint32_t layout_slots(uint32_t subtree_nodes, bool box_leaves) {
+    return box_leaves ? subtree_nodes + (subtree_nodes + 1u) / 2u : subtree_nodes;
+}
 static void emit_layout(const RtbSceneDesc* d, const std::vector<uint32_t>& size, const std::vector<uint32_t>& quad_slot,
-                        int octant, bool ordered, float4* out) {
+                        int octant, bool ordered, float4* out, bool box_leaves = false) {
     if (d->n_nodes == 0) return;
     struct Item {
         int32_t node;
@@ -268,7 +273,7 @@ static void emit_layout(const RtbSceneDesc* d, const std::vector<uint32_t>& size
         const Item it = work.back();
         work.pop_back();
         const RtbBvhNode& nd = d->nodes[it.node];
-        if (nd.leaf >= 0) {
+        if (nd.leaf >= 0 && !box_leaves) {
             leaf_record(d, (uint32_t)nd.leaf, quad_slot, &out[2 * (size_t)it.slot], &out[2 * (size_t)it.slot + 1]);
             continue;
         }
@@ -278,9 +283,13 @@ static void emit_layout(const RtbSceneDesc* d, const std::vector<uint32_t>& size
             lo[a] = neg ? nd.bmax[a] : nd.bmin[a];
             hi[a] = neg ? nd.bmin[a] : nd.bmax[a];
         }
-        const uint32_t skip = it.slot + size[it.node];
+        const uint32_t skip = it.slot + layout_slots(size[it.node], box_leaves);
         out[2 * (size_t)it.slot] = mkf4(lo[0], lo[1], lo[2], bits((KIND_INTERIOR << 30) | skip));
         out[2 * (size_t)it.slot + 1] = mkf4(hi[0], hi[1], hi[2], 0.0f);
+        if (nd.leaf >= 0) {  // box_leaves: {box, skip = slot + 2}, {leaf}
+            leaf_record(d, (uint32_t)nd.leaf, quad_slot, &out[2 * (size_t)it.slot + 2], &out[2 * (size_t)it.slot + 3]);
+            continue;
+        }
         int32_t first = nd.left, second = nd.right;
         if (ordered && octant >= 0) {
             const RtbBvhNode& l = d->nodes[nd.left];
@@ -301,7 +310,7 @@ static void emit_layout(const RtbSceneDesc* d, const std::vector<uint32_t>& size
                 second = nd.left;
             }
         }
-        work.push_back({second, it.slot + 1u + size[first]});
+        work.push_back({second, it.slot + 1u + layout_slots(size[first], box_leaves)});
         work.push_back({first, it.slot + 1u});
     }
 }
@@ -329,6 +338,21 @@ static int32_t build_sah(const RtbSceneDesc* d, const std::vector<uint32_t>& rea
         }
         it.object = nd.leaf;
         items.push_back(it);
+    }
+    // Pad every object box outwards by 2^-21 of the scene's extent on that axis.  The SAH layouts box-test the
+    // leaves too and evaluate the slab test with one FMA per plane (slab_miss_fma); for ray origins inside the scene's
+    // bounds that differs from the exact (plane - origin) * invD by at most 2^-24 * (2|origin| + |plane|) in position,
+    // so with this pad the SAH traversal visits a superset of the leaves an exact test on the host's boxes would.
+    {
+        float extent[3] = {0.0f, 0.0f, 0.0f};
+        for (const Item& it : items)
+            for (int a = 0; a < 3; ++a) extent[a] = std::fmax(extent[a], std::fmax(std::fabs(it.bmin[a]), std::fabs(it.bmax[a])));
+        for (Item& it : items)
+            for (int a = 0; a < 3; ++a) {
+                const float pad = std::ldexp(extent[a], -21);
+                it.bmin[a] -= pad;
+                it.bmax[a] += pad;
+            }
     }
     out.clear();
     if (items.empty()) return -1;
@@ -484,6 +508,7 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     const size_t oct_stride = 2 * ((size_t)n_tree + 1);
     const float4 sentinel = mkf4(0.0f, 0.0f, 0.0f, bits(RTB_META_END));
     std::vector<float4> oct_nodes[3];
+    uint32_t n_tree_sah = 0;
     for (int mode = 0; mode < 2; ++mode) {
         oct_nodes[mode].assign(8 * oct_stride, sentinel);
         for (int oct = 0; oct < 8; ++oct)
@@ -500,9 +525,11 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
         rc = tree_sizes(&sah, sah_size, &sah_depth);
         if (rc != RTB_OK) return rc;
         if (sah.n_nodes != n_tree) return fail(RTB_ERR_INVALID_ARGUMENT, "internal: SAH tree has %u nodes, expected %u", sah.n_nodes, n_tree);
-        oct_nodes[2].assign(8 * oct_stride, sentinel);
+        n_tree_sah = layout_slots(n_tree, true);
+        const size_t sah_stride = 2 * ((size_t)n_tree_sah + 1);
+        oct_nodes[2].assign(8 * sah_stride, sentinel);
         for (int oct = 0; oct < 8; ++oct)
-            emit_layout(&sah, sah_size, quad_slot, oct, true, oct_nodes[2].data() + (size_t)oct * oct_stride);
+            emit_layout(&sah, sah_size, quad_slot, oct, true, oct_nodes[2].data() + (size_t)oct * sah_stride, true);
     }
 
     RtbScene* sc = new (std::nothrow) RtbScene();
@@ -599,6 +626,8 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
         return rc;
     }
     sc->dev.n_nodes = (uint32_t)(nodes.size() / 2);
+    sc->dev.oct_n_nodes[0] = sc->dev.oct_n_nodes[1] = sc->dev.n_nodes;
+    sc->dev.oct_n_nodes[2] = n_tree_sah;
     sc->dev.n_objects = desc->n_hittables;
     sc->dev.has_quads = quads.empty() ? 0u : 1u;
     sc->nodes_fit_smem = sc->dev.n_nodes > 0 && (size_t)sc->dev.n_nodes * 32u <= megakernel_max_smem_nodes_bytes();
@@ -621,7 +650,8 @@ extern "C" int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, u
     std::vector<DevQuad> table;
     for (uint32_t i = 0; i < desc->n_hittables; ++i)
         if (desc->hittables[i].type != RTB_HITTABLE_SPHERE) quad_slot[i] = append_complex(table, desc->hittables[i]);
-    const uint32_t n_tree = desc->n_nodes ? size[desc->root] : 0u;
+    const uint32_t n_host = desc->n_nodes ? size[desc->root] : 0u;
+    const uint32_t n_tree = layout_slots(n_host, mode == RTB_TRAVERSAL_SAH);
     *n_nodes_out = n_tree;
     if (!out_nodes) return RTB_OK;
     std::vector<float4> layout(2 * ((size_t)n_tree + 1), mkf4(0.0f, 0.0f, 0.0f, bits(RTB_META_END)));
@@ -634,7 +664,7 @@ extern "C" int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, u
         std::vector<uint32_t> sah_size;
         rc = tree_sizes(&sah, sah_size, &depth);
         if (rc != RTB_OK) return rc;
-        emit_layout(&sah, sah_size, quad_slot, (int)octant, true, layout.data());
+        emit_layout(&sah, sah_size, quad_slot, (int)octant, true, layout.data(), true);
     } else {
         emit_layout(desc, size, quad_slot, (int)octant, mode == RTB_TRAVERSAL_ORDERED, layout.data());
     }

@@ -61,8 +61,12 @@ struct DevScene {
     // Per-octant layouts for the wavefront integrator, [mode][octant][2 * n_nodes], bounds pre-swapped
     // to (entry plane, exit plane) for the octant.  mode 0 = reference order, 1 = near-child-first,
     // 2 = the same objects re-partitioned by the library with a binned-SAH tree, near-child-first.
-    // Each octant's array holds n_nodes + 1 entries: the last one is the end sentinel (RTB_META_END).
+    // Each octant's array holds oct_n_nodes[mode] + 1 entries: the last one is the end sentinel (RTB_META_END).
+    // Modes 0 and 1 have the host tree's n_nodes entries; mode 2 additionally puts a BOX node (the object's
+    // own bounding box, skip = past the leaf) in front of every leaf, so a leaf is only tested when the ray
+    // enters its box: 3n - 1 entries for n objects.
     const float4* oct_nodes[3];
+    uint32_t oct_n_nodes[3];
     // 4 per object: the leaf record {center1, kind|object}, {center_vec, radius} and the object's material
     // record {m0, m1} inlined (the reference stores Material by value in every Hittable anyway).
     const float4* prims;
@@ -352,6 +356,20 @@ __device__ __forceinline__ bool slab_miss_preswapped(float4 f0, float4 f1, float
     return hi <= lo;
 }
 
+// RTB_TRAVERSAL_SAH only (the library's own tree, whose boxes are padded on the host by more than the
+// rounding difference, see build_sah): the same slab test as one FMA per plane, t = plane * invD - origin * invD.
+// It may only ever ADMIT more nodes than the exact test would; leaves are still tested with the reference's
+// arithmetic, so hit values stay bit-identical.  A NaN (0 * inf) leaves its axis unconstrained.
+__device__ __forceinline__ bool slab_miss_fma(float4 f0, float4 f1, float inv_x, float inv_y, float inv_z, float nox,
+                                              float noy, float noz, float t_min, float t_max) {
+    const float t0x = __fmaf_rn(f0.x, inv_x, nox), t1x = __fmaf_rn(f1.x, inv_x, nox);
+    const float t0y = __fmaf_rn(f0.y, inv_y, noy), t1y = __fmaf_rn(f1.y, inv_y, noy);
+    const float t0z = __fmaf_rn(f0.z, inv_z, noz), t1z = __fmaf_rn(f1.z, inv_z, noz);
+    const float lo = fmaxf(max3f(t0x, t0y, t0z), t_min);
+    const float hi = fminf(min3f(t1x, t1y, t1z), t_max);
+    return hi <= lo;
+}
+
 // Sphere.hit up to the accepted root with a = |direction|^2 hoisted out of the node loop (the
 // reference recomputes the same value at every leaf, src/objects.zig:124).
 __device__ __forceinline__ bool sphere_root_a(float3 o, float3 d, float a, float3 center, float radius, float t_min,
@@ -381,7 +399,7 @@ __device__ __forceinline__ bool sphere_root_a(float3 o, float3 d, float a, float
 #define RTB_META_END 0xffffffffu
 extern __shared__ float4 rtb_smem_nodes[];
 
-template <bool COUNT, bool QUADS, bool SMEM>
+template <bool COUNT, bool QUADS, bool SMEM, bool FMA = false>
 __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ nodes, const DevQuad* __restrict__ quads,
                                                    float3 o, float3 d, float time, float inv_x, float inv_y,
                                                    float inv_z, float t_min, float t_max, uint32_t& n_box,
@@ -394,6 +412,7 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
     best.t = t_max;
     best.node = 0xffffffffu;
     const float a = length_squared(d);
+    const float nox = -(o.x * inv_x), noy = -(o.y * inv_y), noz = -(o.z * inv_z);  // FMA only
     uint32_t i = 0;
     for (;;) {
         float4 f0, f1;
@@ -412,7 +431,9 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
         const uint32_t meta = __float_as_uint(f0.w);
         if (meta < (1u << 30)) {  // KIND_INTERIOR: meta is the skip index
             if (COUNT) ++n_box;
-            i = slab_miss_preswapped(f0, f1, o, inv_x, inv_y, inv_z, t_min, best.t) ? meta : i + 1u;
+            const bool miss = FMA ? slab_miss_fma(f0, f1, inv_x, inv_y, inv_z, nox, noy, noz, t_min, best.t)
+                                  : slab_miss_preswapped(f0, f1, o, inv_x, inv_y, inv_z, t_min, best.t);
+            i = miss ? meta : i + 1u;
         } else {
             if (meta == RTB_META_END) break;
             if (COUNT) ++n_obj;

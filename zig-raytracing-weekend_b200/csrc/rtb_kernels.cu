@@ -56,10 +56,15 @@ __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderPar
                 if (ORDERED) {
                     const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
                     const float4* oct =
-                        P.scene.oct_nodes[P.ordered] + (size_t)ray_octant(ix, iy, iz) * 2u * (P.scene.n_nodes + 1u);
-                    best = traverse_octant<COUNT, QUADS, false>(oct, P.scene.quads, ray.o, ray.d, ray.time, ix, iy, iz,
-                                                                0.001f, __int_as_float(0x7f800000), n_box, n_obj, 0u,
-                                                                key, segment);
+                        P.scene.oct_nodes[P.ordered] + (size_t)ray_octant(ix, iy, iz) * 2u * (P.scene.oct_n_nodes[P.ordered] + 1u);
+                    if (P.ordered == 2u)
+                        best = traverse_octant<COUNT, QUADS, false, true>(oct, P.scene.quads, ray.o, ray.d, ray.time, ix,
+                                                                          iy, iz, 0.001f, __int_as_float(0x7f800000),
+                                                                          n_box, n_obj, 0u, key, segment);
+                    else
+                        best = traverse_octant<COUNT, QUADS, false>(oct, P.scene.quads, ray.o, ray.d, ray.time, ix, iy, iz,
+                                                                    0.001f, __int_as_float(0x7f800000), n_box, n_obj, 0u,
+                                                                    key, segment);
                 } else {
                     best = traverse_reference<COUNT, QUADS>(nodes, P.scene.n_nodes, P.scene.quads, ray, 0.001f,
                                                             __int_as_float(0x7f800000), n_box, n_obj, key, segment);
@@ -183,9 +188,13 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     Nearest best;
     if (ORDERED) {
         const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
-        const float4* oct = scene.oct_nodes[layout] + (size_t)ray_octant(ix, iy, iz) * 2u * (scene.n_nodes + 1u);
-        best = traverse_octant<true, QUADS, false>(oct, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min, rr.t_max,
-                                                   n_box, n_obj, 0u, qkey, 1u);
+        const float4* oct = scene.oct_nodes[layout] + (size_t)ray_octant(ix, iy, iz) * 2u * (scene.oct_n_nodes[layout] + 1u);
+        if (layout == 2u)
+            best = traverse_octant<true, QUADS, false, true>(oct, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min,
+                                                             rr.t_max, n_box, n_obj, 0u, qkey, 1u);
+        else
+            best = traverse_octant<true, QUADS, false>(oct, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min, rr.t_max,
+                                                       n_box, n_obj, 0u, qkey, 1u);
     } else {
         best = traverse_reference<true, QUADS>(scene.nodes, scene.n_nodes, scene.quads, r, rr.t_min, rr.t_max, n_box,
                                                n_obj, qkey, 1u);

@@ -31,7 +31,25 @@ namespace rtb {
 
 constexpr uint32_t kOctants = 8;
 constexpr uint32_t kBins = 8;     // counters per binned queue set (8 octants; 5 shading classes, padded)
-constexpr uint32_t kChunk = 256;  // rays per CTA pass
+constexpr uint32_t kChunk = 256;  // hit records per CTA pass of wf_shade
+// Threads (= rays per CTA pass) of wf_extend.  The octant layout staged in shared memory is shared by the whole CTA,
+// so a larger CTA amortises it: with the 47 KB Book-1 SAH layout 256 threads allow 4 CTAs = 1024 threads per SM,
+// 512 threads allow 3 CTAs = 1536.
+#ifndef RTB_EXTEND_THREADS
+#define RTB_EXTEND_THREADS 512
+#endif
+constexpr uint32_t kExtendThreads = RTB_EXTEND_THREADS;
+#ifndef RTB_EXTEND_GRID_PER_SM
+#define RTB_EXTEND_GRID_PER_SM 4
+#endif
+#ifndef RTB_SHADE_GRID_PER_SM
+#define RTB_SHADE_GRID_PER_SM 8
+#endif
+// wf_shade is bound by DRAM latency (gathers of 32-byte records): 5 CTAs per SM (<= 48 registers) instead of the 4
+// that 64 registers allow measured +7 % on the whole step.
+#ifndef RTB_SHADE_MINBLOCKS
+#define RTB_SHADE_MINBLOCKS 5
+#endif
 
 // 32-byte records everywhere (= one DRAM sector), because the shade kernel GATHERS them: ncu (r1e) showed
 // it DRAM-bound at ~50 % of HBM peak fetching 16 B pieces out of separate arrays, two sectors per 32 B used.
@@ -43,7 +61,7 @@ struct WfQueue {
 struct WfLane {
     size_t capacity = 0;  // slots
     WfQueue q[2]{};
-    uint4* hitq = nullptr;       // [class][capacity] {ray position, bits(t), object, -}
+    uint4* hitq = nullptr;       // [class][capacity] {ray position, bits(t), object, path slot}
     float4* TL = nullptr;        // [capacity][2]: {T.xyz, L.x}, {L.y, L.z, -, -}: throughput and radiance so far
                                  // (the final radiance once the path has ended)
     uint32_t* counts = nullptr;  // [2][8] ray-queue sizes, then [2][8] hit-queue sizes
@@ -51,7 +69,13 @@ struct WfLane {
     cudaEvent_t accumulated = nullptr;  // recorded after this lane's wf_accumulate
 };
 
-constexpr int kLanes = 3;
+#ifndef RTB_WF_LANES
+#define RTB_WF_LANES 4
+#endif
+#ifndef RTB_WF_BATCH_LOG2
+#define RTB_WF_BATCH_LOG2 23
+#endif
+constexpr int kLanes = RTB_WF_LANES;
 
 struct WavefrontState {
     WfLane lanes[kLanes];
@@ -121,13 +145,14 @@ struct ChunkMap {
     uint32_t count[kBins];
     uint32_t first_chunk[kBins + 1];
 };
-__device__ __forceinline__ void chunk_map_init(ChunkMap& m, const uint32_t* counts, uint32_t n_bins) {
+__device__ __forceinline__ void chunk_map_init(ChunkMap& m, const uint32_t* counts, uint32_t n_bins,
+                                               uint32_t chunk = kChunk) {
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
         for (uint32_t b = 0; b < kBins; ++b) {
             m.count[b] = b < n_bins ? counts[b] : 0u;
             m.first_chunk[b] = acc;
-            acc += (m.count[b] + kChunk - 1u) / kChunk;
+            acc += (m.count[b] + chunk - 1u) / chunk;
         }
         m.first_chunk[kBins] = acc;
     }
@@ -164,11 +189,12 @@ __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
 
 // One thread per ray, plain node loop over the octant's layout; the result goes to the hit queue of
 // the hit object's shading class.
-template <bool SMEM_NODES, bool COUNT, bool QUADS>
-__global__ void __launch_bounds__(256) wf_extend(const WfParams P) {
+// FMA: the layout is the library's own padded SAH tree (mode 2), whose slab test may use one FMA per plane.
+template <bool SMEM_NODES, bool COUNT, bool QUADS, bool FMA>
+__global__ void __launch_bounds__(kExtendThreads) wf_extend(const WfParams P) {
     __shared__ ChunkMap map;
-    const uint32_t n_nodes = P.R.scene.n_nodes;
-    chunk_map_init(map, P.count_in, kOctants);
+    const uint32_t n_nodes = P.R.scene.oct_n_nodes[P.R.ordered];
+    chunk_map_init(map, P.count_in, kOctants, kExtendThreads);
     // Bins nobody reads during this kernel: the ray bins this bounce's shade kernel will push into and
     // the hit bins of the next bounce.
     if (blockIdx.x == 0 && threadIdx.x < kBins) {
@@ -191,7 +217,7 @@ __global__ void __launch_bounds__(256) wf_extend(const WfParams P) {
             __syncthreads();
             staged = oct;
         }
-        const uint32_t i = (c - map.first_chunk[oct]) * kChunk + threadIdx.x;
+        const uint32_t i = (c - map.first_chunk[oct]) * kExtendThreads + threadIdx.x;
         const bool valid = i < map.count[oct];
         uint32_t cls = CLASS_MISS;
         uint4 entry = make_uint4(0u, 0u, 0u, 0u);
@@ -208,11 +234,11 @@ __global__ void __launch_bounds__(256) wf_extend(const WfParams P) {
                 slot_pixel(P.R, slot % P.slots_per_sample, key.pixel);
                 key.sample = P.batch_begin + slot / P.slots_per_sample;
             }
-            const Nearest best = traverse_octant<COUNT, QUADS, SMEM_NODES>(
+            const Nearest best = traverse_octant<COUNT, QUADS, SMEM_NODES, FMA>(
                 nodes, P.R.scene.quads, o, d, a.w, 1.0f / d.x, 1.0f / d.y, 1.0f / d.z, 0.001f, __int_as_float(0x7f800000),
                 n_box, n_obj, smem_base, key, P.segment);
             if (best.node != 0xffffffffu) cls = P.R.scene.object_class[best.node];
-            entry = make_uint4((uint32_t)at, __float_as_uint(best.t), best.node, 0u);
+            entry = make_uint4((uint32_t)at, __float_as_uint(best.t), best.node, __float_as_uint(b.w));
         }
         const uint32_t j = queue_reserve(P.hit_count, valid, cls);
         if (valid) P.hitq[(size_t)cls * P.capacity + j] = entry;
@@ -226,7 +252,7 @@ __global__ void __launch_bounds__(256) wf_extend(const WfParams P) {
 
 // One thread per hit record; every 256-record chunk belongs to one shading class.
 template <bool COUNT, bool QUADS>
-__global__ void __launch_bounds__(256) wf_shade(const WfParams P) {
+__global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfParams P) {
     __shared__ ChunkMap map;
     chunk_map_init(map, P.hit_count, kShadeClasses);
     const uint32_t total_chunks = map.first_chunk[kBins];
@@ -248,7 +274,7 @@ __global__ void __launch_bounds__(256) wf_shade(const WfParams P) {
             r.o = f3(a);
             r.time = a.w;
             r.d = f3(b);
-            slot = __float_as_uint(b.w);
+            slot = e.w;  // == bits(b.w); carried in the hit record so that the (T, L) gather does not wait for the ray
             const float4 tl0 = P.TL[2u * (size_t)slot];
             const float4 tl1 = P.TL[2u * (size_t)slot + 1u];
             float3 T = f3(tl0);
@@ -359,20 +385,25 @@ static cudaError_t lane_reserve(WfLane* ln, size_t capacity) {
     return cudaSuccess;
 }
 
-template <bool COUNT, bool QUADS>
-static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
+template <bool COUNT, bool QUADS, bool FMA>
+static cudaError_t wf_launch_extend_fma(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
     if (smem_nodes) {
-        const size_t smem = ((size_t)P.R.scene.n_nodes + 1u) * 32u;
-        auto k = wf_extend<true, COUNT, QUADS>;
+        const size_t smem = ((size_t)P.R.scene.oct_n_nodes[P.R.ordered] + 1u) * 32u;
+        auto k = wf_extend<true, COUNT, QUADS, FMA>;
         if (smem > 40u * 1024u) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        k<<<grid, 256, smem, stream>>>(P);
+        k<<<grid, kExtendThreads, smem, stream>>>(P);
     } else {
-        wf_extend<false, COUNT, QUADS><<<grid, 256, 0, stream>>>(P);
+        wf_extend<false, COUNT, QUADS, FMA><<<grid, kExtendThreads, 0, stream>>>(P);
     }
     return cudaGetLastError();
+}
+template <bool COUNT, bool QUADS>
+static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
+    return P.R.ordered == 2u ? wf_launch_extend_fma<COUNT, QUADS, true>(P, smem_nodes, grid, stream)
+                             : wf_launch_extend_fma<COUNT, QUADS, false>(P, smem_nodes, grid, stream);
 }
 
 // Batches of ~8 M paths are pipelined over kLanes streams.  After the first ~10 bounces a batch is a
@@ -393,7 +424,7 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     if (e != cudaSuccess) return e;
     const uint32_t slots_per_sample = owned * kCtaThreads;
     // Samples in flight per pixel and batch (624 B of queue/state per path slot: 5.2 GB per lane at 8 M).
-    const uint64_t target_paths = 8ull << 20;
+    const uint64_t target_paths = 1ull << RTB_WF_BATCH_LOG2;
     uint32_t B = (uint32_t)((target_paths + slots_per_sample - 1) / slots_per_sample);
     if (B < 1u) B = 1u;
     if (B > p.sample_count) B = p.sample_count;
@@ -407,7 +438,7 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     }
 
     const bool smem_nodes =
-        p.scene.n_nodes > 0 && ((size_t)p.scene.n_nodes + 1u) * 32u <= megakernel_max_smem_nodes_bytes();
+        p.scene.n_nodes > 0 && ((size_t)p.scene.oct_n_nodes[p.ordered] + 1u) * 32u <= megakernel_max_smem_nodes_bytes();
     const bool quads = p.scene.has_quads != 0u;
     const uint32_t max_grid = (uint32_t)st->sm_count * 8u;
 
@@ -440,6 +471,10 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         P.count_out = ln.counts + cur * kBins;
         uint32_t grid = (cap + 255u) / 256u + kBins;  // chunks: every bin may end with a partial one
         if (grid > max_grid) grid = max_grid;
+        uint32_t grid_e = (cap + kExtendThreads - 1u) / kExtendThreads + kBins;
+        if (grid_e > (uint32_t)st->sm_count * RTB_EXTEND_GRID_PER_SM) grid_e = (uint32_t)st->sm_count * RTB_EXTEND_GRID_PER_SM;
+        uint32_t grid_s = (cap + 255u) / 256u + kBins;
+        if (grid_s > (uint32_t)st->sm_count * RTB_SHADE_GRID_PER_SM) grid_s = (uint32_t)st->sm_count * RTB_SHADE_GRID_PER_SM;
         wf_raygen<<<grid, 256, 0, ln.stream>>>(P);
         ++launches;
         for (uint32_t bounce = 0; bounce < p.cam.max_depth; ++bounce) {
@@ -452,9 +487,9 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
             P.segment = bounce + 1u;
 #define RTB_WF(C, Q)                                                      \
     do {                                                                  \
-        e = wf_launch_extend<C, Q>(P, smem_nodes, grid, ln.stream);       \
+        e = wf_launch_extend<C, Q>(P, smem_nodes, grid_e, ln.stream);     \
         if (e == cudaSuccess) {                                           \
-            wf_shade<C, Q><<<grid, 256, 0, ln.stream>>>(P);               \
+            wf_shade<C, Q><<<grid_s, 256, 0, ln.stream>>>(P);             \
             e = cudaGetLastError();                                       \
         }                                                                 \
     } while (0)
@@ -466,7 +501,10 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
             cur ^= 1;
             // Later bounces hold a small fraction of the rays: a smaller grid keeps the (mostly empty)
             // launches cheap.  Correct for any count: the kernels stride over the whole queue.
-            if (bounce == 7u && grid > (uint32_t)st->sm_count * 2u) grid = (uint32_t)st->sm_count * 2u;
+            if (bounce == 7u) {
+                if (grid_s > (uint32_t)st->sm_count * 2u) grid_s = (uint32_t)st->sm_count * 2u;
+                if (grid_e > (uint32_t)st->sm_count) grid_e = (uint32_t)st->sm_count;
+            }
         }
         if (prev_lane >= 0 && prev_lane != lane_id) {
             e = cudaStreamWaitEvent(ln.stream, st->lanes[prev_lane].accumulated, 0);
