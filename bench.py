@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
+                    help="N>1 exchange step: p2p = fused reduce+resolve kernel over peer memory (rtb_exchange_resolve), "
+                         "nccl = NCCL sum-reduce to rank 0 then rtb_resolve_device")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank renders --spp samples (sample partition only); strong: the ranks share "
                          "--spp samples (samples) or the frame's tiles (tiles) — e.g. BASELINE config 5: "
@@ -209,8 +212,24 @@ def run_ours(a):
     stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream
 
-    d_acc = torch.zeros(npx, 4, device=dev, dtype=torch.float32)
-    d_rgba = torch.zeros(npx, 4, device=dev, dtype=torch.uint8)
+    px = None
+    if world_size > 1 and a.exchange == "p2p":
+        # per-rank buffers owned by the library and mapped into every rank (CUDA IPC over NVLink/NVSwitch)
+        px = mg.PeerExchange(npx, rank, world_size, local_rank)
+        d_acc, d_rgba = px.accum, px.rgba
+    else:
+        d_acc = torch.zeros(npx, 4, device=dev, dtype=torch.float32)
+        d_rgba = torch.zeros(npx, 4, device=dev, dtype=torch.uint8)
+
+    def exchange_and_resolve(part):
+        """The exchange step + resolve: afterwards rank 0 holds the combined sums and the RGBA8 frame."""
+        if px is not None:
+            px.exchange(float(part.total_samples), sptr)
+            return
+        mg.combine(d_acc, part, fix_w=False)
+        if rank == 0:
+            p._check(p._ffi.rtb().rtb_resolve_device(d_acc.data_ptr(), d_rgba.data_ptr(), npx,
+                                                     float(part.total_samples), local_rank, sptr), "rtb_resolve_device")
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 
     traversal = {"reference": p.RTB_TRAVERSAL_REFERENCE, "ordered": p.RTB_TRAVERSAL_ORDERED,
@@ -228,10 +247,7 @@ def run_ours(a):
         o, part = make_options(step, integrator, p.RTB_FLAG_COUNT_WORK if count else 0, spp, trav)
         d_acc.zero_()
         st = scene.render_device(cam, o, d_acc.data_ptr(), sptr, want_stats=count)
-        mg.combine(d_acc, part, fix_w=False)
-        if rank == 0:
-            p._check(p._ffi.rtb().rtb_resolve_device(d_acc.data_ptr(), d_rgba.data_ptr(), npx,
-                                                     float(part.total_samples), local_rank, sptr), "rtb_resolve_device")
+        exchange_and_resolve(part)
         return st
 
     # -- integrator choice: measured, not assumed (north_star: pick from evidence) -------------------------------
@@ -281,7 +297,7 @@ def run_ours(a):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(a.steps)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     if world_size > 1:
@@ -295,21 +311,21 @@ def run_ours(a):
         ev[k][0].record(stream)
         scene.render_device(cam, o, d_acc.data_ptr(), sptr, want_stats=False)
         ev[k][1].record(stream)
-        mg.combine(d_acc, part, fix_w=False)
-        if rank == 0:
-            p._check(p._ffi.rtb().rtb_resolve_device(d_acc.data_ptr(), d_rgba.data_ptr(), npx,
-                                                     float(part.total_samples), local_rank, sptr), "rtb_resolve_device")
+        exchange_and_resolve(part)
+        ev[k][2].record(stream)
     e_end.record(stream)
     torch.cuda.synchronize(dev)
     if world_size > 1:
         dist.barrier()
     total_ms = e_begin.elapsed_time(e_end)
-    kernel_ms = sum(b.elapsed_time(e) for b, e in ev) / a.steps
+    kernel_ms = sum(b.elapsed_time(e) for b, e, _ in ev) / a.steps
+    exchange_ms = sum(e.elapsed_time(x) for _, e, x in ev) / a.steps   # includes waiting for the slowest rank
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([total_ms, kernel_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([total_ms, kernel_ms, -exchange_ms], device=dev, dtype=torch.float64)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kernel_ms = t.tolist()
+    total_ms, kernel_ms, exchange_ms = t.tolist()
+    exchange_ms = -exchange_ms   # MIN over ranks: the rank that arrives last sees the exchange without the wait
 
     weak = a.partition == "samples" and a.scaling == "weak"
     paths_per_step = npx * a.spp * (world_size if weak else 1)
@@ -353,11 +369,8 @@ def run_ours(a):
                 h_acc.zero_()
                 d_acc.copy_(h_acc, non_blocking=True)
                 scene.render_device(cam, o, d_acc.data_ptr(), sptr, want_stats=False)
-                mg.combine(d_acc, part, fix_w=False)
+                exchange_and_resolve(part)
                 if rank == 0:
-                    p._check(p._ffi.rtb().rtb_resolve_device(d_acc.data_ptr(), d_rgba.data_ptr(), npx,
-                                                             float(part.total_samples), local_rank, sptr),
-                             "rtb_resolve_device")
                     h_acc.copy_(d_acc, non_blocking=True)
                     h_rgba.copy_(d_rgba, non_blocking=True)
                 torch.cuda.synchronize(dev)
@@ -376,8 +389,12 @@ def run_ours(a):
         e2e = {"value": paths_per_step * a.steps / dt.item() / 1e6, "unit": "Mpaths/s",
                "h2d_bytes_per_step": 16 * npx, "d2h_bytes_per_step": 20 * npx,
                "api": "rtb_render (host buffers)" if world_size == 1 else
-                      "H2D + rtb_render_device + NCCL reduce + rtb_resolve_device + D2H"}
+                      ("H2D + rtb_render_device + rtb_exchange_resolve (peer memory) + D2H" if px is not None else
+                       "H2D + rtb_render_device + NCCL reduce + rtb_resolve_device + D2H")}
 
+    if px is not None:
+        d_acc = d_rgba = None
+        px.close()
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()
@@ -435,6 +452,10 @@ def run_ours(a):
         "mrays_per_s": value * cst["n_rays"] / cst["n_paths"],
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "integrator_probe": probe, "variants_mpaths_per_s": variants,
+        "exchange": None if world_size == 1 else {
+            "kind": "rtb_exchange_resolve: fused reduce-scatter + resolve + gather over peer memory, one kernel per rank"
+                    if a.exchange == "p2p" else "NCCL reduce(sum) to rank 0 + rtb_resolve_device",
+            "ms_per_step": exchange_ms, "bytes_per_rank": 16 * npx},
     }
     print(json.dumps(out))
     if world_size > 1:

@@ -324,6 +324,38 @@ int rtb_resolve_device(const float* d_accum, uint8_t* d_rgba, uint64_t n_pixels,
 /* Host-buffer convenience form of the resolve (copies in, resolves on the GPU, copies out). */
 int rtb_resolve(const float* accum, uint8_t* rgba, uint64_t n_pixels, float n_samples_override, int device);
 
+/* ---- multi-GPU exchange over peer memory (one process per GPU) --------------------------------------
+ * The reference's 8 render threads write disjoint strips of ONE buffer (src/main.zig:318-323, src/camera.zig:93-99);
+ * across GPUs the strips become per-rank accumulation buffers that are combined once per render.  These calls let the
+ * ranks map each other's buffers (CUDA IPC over NVLink/NVSwitch) and run the combine as ONE kernel per rank that also
+ * does the resolve.  The rendezvous (exchanging the 64-byte handles, the barrier around the kernel) is the caller's:
+ * torch.distributed / NCCL in this repo (zig-raytracing-weekend_b200/multigpu.py), any transport for a Zig host. */
+typedef struct RtbIpcHandle {
+    uint8_t bytes[64]; /* cudaIpcMemHandle_t */
+} RtbIpcHandle;
+
+/* Device memory that can be exported to other processes (a cudaMalloc allocation of its own). */
+int rtb_buffer_alloc(int device, uint64_t bytes, void** device_ptr_out);
+int rtb_buffer_free(int device, void* device_ptr);
+int rtb_ipc_export(int device, const void* device_ptr, RtbIpcHandle* handle_out);
+/* Maps a buffer exported by ANOTHER process into this one (peer access is enabled as needed). */
+int rtb_ipc_open(int device, const RtbIpcHandle* handle, void** device_ptr_out);
+int rtb_ipc_close(int device, void* device_ptr);
+
+/* Slice of the frame that rank `rank` of `world` combines: [*begin_out, *end_out), 256-pixel aligned. */
+int rtb_exchange_slice(uint64_t n_pixels, uint32_t world, uint32_t rank, uint64_t* begin_out, uint64_t* end_out);
+
+/* Fused exchange + resolve.  peer_accum[r] = rank r's float4 accumulation buffer as mapped into this process
+ * (peer_accum[rank] is this rank's own buffer).  For the pixels of this rank's slice: sum over r in rank order
+ * (x, y, z), .w = samples_per_pixel, toGamma2 + truncation; the sums go to root_accum_out and the pixels to
+ * root_rgba_out — the ROOT rank's buffers as mapped into this process (root_accum_out may be peer_accum[root]: in
+ * place).  Asynchronous on `cuda_stream`.  All ranks must have finished rendering before any rank's launch starts and
+ * nobody may touch the buffers again before every rank's launch has finished: bracket it with a stream-ordered
+ * barrier (e.g. a 1-element NCCL all-reduce on the same stream). */
+int rtb_exchange_resolve(const float* const* peer_accum, uint32_t world, uint32_t rank, float* root_accum_out,
+                         uint8_t* root_rgba_out, uint64_t n_pixels, float samples_per_pixel, int device,
+                         void* cuda_stream);
+
 /* Progressive / cancellable render, preserving the GUI behaviour of the reference (progress
  * polling: countSamples src/main.zig:470-477; STOP: stopRender :328-336; per-sample refresh of
  * texture_buffer: src/camera.zig:57-65).  A worker thread renders `samples_per_launch` samples at

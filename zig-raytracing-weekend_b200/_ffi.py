@@ -127,11 +127,16 @@ HIT_DTYPE = [("object", "<i4"), ("front_face", "<u4"), ("t", "<f4"), ("p", "<f4"
              ("u", "<f4"), ("v", "<f4"), ("n_box_tests", "<u4"), ("n_object_tests", "<u4")]
 
 # Every symbol include/rtb.h and include/rtw_host.h declare (checked by the CPU test-suite).
+class RtbIpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 64)]
+
+
 RTB_SYMBOLS = [
     "rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_scene_create", "rtb_scene_destroy",
     "rtb_trace_rays", "rtb_render", "rtb_render_device", "rtb_resolve_device", "rtb_resolve", "rtb_render_async",
     "rtb_job_progress", "rtb_job_cancel", "rtb_job_wait", "rtb_job_destroy", "rtb_philox_device_selftest",
-    "rtb_measure_fp32_peak", "rtb_debug_build_layout",
+    "rtb_measure_fp32_peak", "rtb_debug_build_layout", "rtb_buffer_alloc", "rtb_buffer_free", "rtb_ipc_export",
+    "rtb_ipc_open", "rtb_ipc_close", "rtb_exchange_slice", "rtb_exchange_resolve",
 ]
 RTW_SYMBOLS = [
     "rtw_world_create", "rtw_world_new", "rtw_world_add_image", "rtw_world_add_sphere", "rtw_world_add_quad",
@@ -180,6 +185,13 @@ def rtb() -> C.CDLL:
     lib.rtb_philox_device_selftest.argtypes = [vp, vp, u32, vp, C.c_int]
     lib.rtb_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.rtb_debug_build_layout.argtypes = [C.POINTER(RtbSceneDesc), u32, u32, vp, C.POINTER(u32)]
+    lib.rtb_buffer_alloc.argtypes = [C.c_int, u64, C.POINTER(vp)]
+    lib.rtb_buffer_free.argtypes = [C.c_int, vp]
+    lib.rtb_ipc_export.argtypes = [C.c_int, vp, C.POINTER(RtbIpcHandle)]
+    lib.rtb_ipc_open.argtypes = [C.c_int, C.POINTER(RtbIpcHandle), C.POINTER(vp)]
+    lib.rtb_ipc_close.argtypes = [C.c_int, vp]
+    lib.rtb_exchange_slice.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
+    lib.rtb_exchange_resolve.argtypes = [C.POINTER(vp), u32, u32, vp, vp, u64, f32, C.c_int, vp]
     for s in RTB_SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("rtb_abi_version", "rtb_last_error"):

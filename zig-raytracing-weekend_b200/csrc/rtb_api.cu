@@ -830,6 +830,91 @@ extern "C" int rtb_resolve_device(const float* d_accum, uint8_t* d_rgba, uint64_
     return RTB_OK;
 }
 
+// ---- multi-GPU exchange over peer memory ------------------------------------------------------------------------
+extern "C" int rtb_buffer_alloc(int device, uint64_t bytes, void** device_ptr_out) {
+    if (!device_ptr_out) return fail(RTB_ERR_INVALID_ARGUMENT, "device_ptr_out is NULL");
+    *device_ptr_out = nullptr;
+    RTB_CUDA(cudaSetDevice(device));
+    void* p = nullptr;
+    const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(exchange buffer)");
+    *device_ptr_out = p;
+    return RTB_OK;
+}
+
+extern "C" int rtb_buffer_free(int device, void* device_ptr) {
+    if (!device_ptr) return RTB_OK;
+    RTB_CUDA(cudaSetDevice(device));
+    RTB_CUDA(cudaFree(device_ptr));
+    return RTB_OK;
+}
+
+extern "C" int rtb_ipc_export(int device, const void* device_ptr, RtbIpcHandle* handle_out) {
+    if (!device_ptr || !handle_out) return fail(RTB_ERR_INVALID_ARGUMENT, "device_ptr/handle_out is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(RtbIpcHandle), "RtbIpcHandle must hold a cudaIpcMemHandle_t");
+    RTB_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    RTB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr)));
+    std::memcpy(handle_out->bytes, &h, sizeof(h));
+    return RTB_OK;
+}
+
+extern "C" int rtb_ipc_open(int device, const RtbIpcHandle* handle, void** device_ptr_out) {
+    if (!handle || !device_ptr_out) return fail(RTB_ERR_INVALID_ARGUMENT, "handle/device_ptr_out is NULL");
+    *device_ptr_out = nullptr;
+    RTB_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle->bytes, sizeof(h));
+    void* p = nullptr;
+    RTB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *device_ptr_out = p;
+    return RTB_OK;
+}
+
+extern "C" int rtb_ipc_close(int device, void* device_ptr) {
+    if (!device_ptr) return RTB_OK;
+    RTB_CUDA(cudaSetDevice(device));
+    RTB_CUDA(cudaIpcCloseMemHandle(device_ptr));
+    return RTB_OK;
+}
+
+extern "C" int rtb_exchange_slice(uint64_t n_pixels, uint32_t world, uint32_t rank, uint64_t* begin_out,
+                                  uint64_t* end_out) {
+    if (!begin_out || !end_out) return fail(RTB_ERR_INVALID_ARGUMENT, "begin_out/end_out is NULL");
+    if (world == 0 || rank >= world) return fail(RTB_ERR_INVALID_ARGUMENT, "rank %u out of range (world %u)", rank, world);
+    uint64_t per = (n_pixels + world - 1) / world;
+    per = (per + 255u) / 256u * 256u;
+    uint64_t b = per * rank, e = per * (rank + 1ull);
+    if (b > n_pixels) b = n_pixels;
+    if (e > n_pixels) e = n_pixels;
+    *begin_out = b;
+    *end_out = e;
+    return RTB_OK;
+}
+
+extern "C" int rtb_exchange_resolve(const float* const* peer_accum, uint32_t world, uint32_t rank, float* root_accum_out,
+                                    uint8_t* root_rgba_out, uint64_t n_pixels, float samples_per_pixel, int device,
+                                    void* cuda_stream) {
+    if (world == 0 || world > kMaxPeers || rank >= world)
+        return fail(RTB_ERR_INVALID_ARGUMENT, "world %u / rank %u out of range (max %u ranks)", world, rank, kMaxPeers);
+    if (!peer_accum || !root_accum_out || !root_rgba_out) return fail(RTB_ERR_INVALID_ARGUMENT, "NULL buffer");
+    if (!(samples_per_pixel > 0.0f)) return fail(RTB_ERR_INVALID_ARGUMENT, "samples_per_pixel must be > 0");
+    PeerAccums peers{};
+    for (uint32_t r = 0; r < world; ++r) {
+        if (!peer_accum[r]) return fail(RTB_ERR_INVALID_ARGUMENT, "peer_accum[%u] is NULL", r);
+        peers.p[r] = reinterpret_cast<const float4*>(peer_accum[r]);
+    }
+    uint64_t begin = 0, end = 0;
+    const int rc = rtb_exchange_slice(n_pixels, world, rank, &begin, &end);
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaSetDevice(device));
+    const cudaError_t e = launch_exchange_resolve(peers, world, reinterpret_cast<float4*>(root_accum_out),
+                                                  reinterpret_cast<uchar4*>(root_rgba_out), begin, end, samples_per_pixel,
+                                                  static_cast<cudaStream_t>(cuda_stream));
+    if (e != cudaSuccess) return cuda_fail(e, "launch_exchange_resolve");
+    return RTB_OK;
+}
+
 extern "C" int rtb_resolve(const float* accum, uint8_t* rgba, uint64_t n_pixels, float n_samples_override, int device) {
     if (n_pixels && (!accum || !rgba)) return fail(RTB_ERR_INVALID_ARGUMENT, "accum/rgba is NULL");
     if (n_pixels == 0) return RTB_OK;

@@ -258,6 +258,65 @@ cudaError_t launch_resolve(const float4* d_accum, uchar4* d_rgba, uint64_t n_pix
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// K5 — fused exchange + resolve over peer memory (multi-GPU).
+//
+// Every rank owns one contiguous slice of the frame.  For its slice it loads the float4 accumulators of ALL ranks
+// (its own from local HBM, the others with plain loads through NVLink/NVSwitch peer mappings), adds them in rank
+// order (deterministic), sets .w to the frame's samples per pixel, applies toGamma2 + quantisation and stores the
+// sums and the RGBA8 pixels straight into the root rank's buffers (peer stores).  That is reduce-scatter + resolve +
+// gather in one pass: every byte crosses NVLink once, no GPU receives more than (world-1)/world of a frame, and the
+// resolve costs no extra trip through HBM.  The caller brackets the launch with a stream-ordered barrier.
+// ------------------------------------------------------------------------------------------
+template <int WORLD>
+__global__ void __launch_bounds__(256) exchange_resolve_kernel(const PeerAccums peers, uint32_t world,
+                                                               float4* root_accum,  // may alias peers.p[root]
+                                                               uchar4* __restrict__ root_rgba, uint64_t begin,
+                                                               uint64_t end, float samples_per_pixel) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+        float4 v[WORLD > 0 ? WORLD : 1];
+        float4 s;
+        if (WORLD > 0) {
+#pragma unroll
+            for (int r = 0; r < WORLD; ++r) v[r] = peers.p[r][i];  // all loads in flight before the first add
+            s = v[0];
+#pragma unroll
+            for (int r = 1; r < WORLD; ++r) {
+                s.x += v[r].x;
+                s.y += v[r].y;
+                s.z += v[r].z;
+            }
+        } else {
+            s = peers.p[0][i];
+            for (uint32_t r = 1; r < world; ++r) {
+                const float4 t = peers.p[r][i];
+                s.x += t.x;
+                s.y += t.y;
+                s.z += t.z;
+            }
+        }
+        s.w = samples_per_pixel;
+        root_accum[i] = s;
+        root_rgba[i] = quantise(s, samples_per_pixel);
+    }
+}
+
+cudaError_t launch_exchange_resolve(const PeerAccums& peers, uint32_t world, float4* root_accum, uchar4* root_rgba,
+                                    uint64_t begin, uint64_t end, float samples_per_pixel, cudaStream_t stream) {
+    if (end <= begin) return cudaSuccess;
+    uint64_t blocks = (end - begin + 255u) / 256u;
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    const uint32_t g = (uint32_t)blocks;
+    switch (world) {
+        case 2: exchange_resolve_kernel<2><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel); break;
+        case 4: exchange_resolve_kernel<4><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel); break;
+        case 8: exchange_resolve_kernel<8><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel); break;
+        default: exchange_resolve_kernel<0><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel); break;
+    }
+    return cudaGetLastError();
+}
+
 __global__ void philox_selftest_kernel(const uint4* __restrict__ ctr, uint2 key, uint32_t n, uint4* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = philox4x32_10(ctr[i], key);

@@ -39,6 +39,14 @@ cudaError_t launch_trace(const DevScene& scene, const RtbRay* d_rays, uint64_t n
 cudaError_t launch_resolve(const float4* d_accum, uchar4* d_rgba, uint64_t n_pixels, float n_override,
                            cudaStream_t stream);
 
+// K5: fused multi-GPU exchange + resolve over peer memory (one launch per rank, its slice [begin, end)).
+constexpr uint32_t kMaxPeers = 16;
+struct PeerAccums {
+    const float4* p[kMaxPeers];  // accumulators of rank 0..world-1 as mapped into THIS process
+};
+cudaError_t launch_exchange_resolve(const PeerAccums& peers, uint32_t world, float4* root_accum, uchar4* root_rgba,
+                                    uint64_t begin, uint64_t end, float samples_per_pixel, cudaStream_t stream);
+
 cudaError_t launch_philox_selftest(const uint4* d_ctr, uint2 key, uint32_t n, uint4* d_out, cudaStream_t stream);
 
 // FFMA-chain microbenchmark (roofline denominator): out must hold grid*256 floats.

@@ -7,8 +7,13 @@ src/camera.zig:93-99).  Here the scene is replicated on every GPU and the work i
     single GPU would trace; perfectly balanced; or
   * interleaved 32x8-pixel TILES ("tiles"): rank r renders tiles t with t % world == r — disjoint pixels.
 Either way every rank ends up with a float4 accumulation buffer of the full frame (zero where it rendered
-nothing) and ONE collective combines them: a sum-reduce to rank 0 over NCCL/NVLink (gloo on CPU in tests),
-BEFORE gamma and quantisation, which then run once on rank 0 (rtb_resolve_device).
+nothing) and ONE exchange step combines them BEFORE gamma and quantisation:
+  * `PeerExchange` (the product path on a multi-GPU node): the ranks map each other's buffers (CUDA IPC over
+    NVLink/NVSwitch) and each runs ONE kernel (rtb_exchange_resolve) that sums its slice of the frame over all
+    ranks, resolves it and stores sums + RGBA8 straight into rank 0's buffers — reduce-scatter + resolve + gather
+    fused; torch.distributed only carries the 64-byte handles and the barrier around the kernel;
+  * `combine` (NCCL sum-reduce to rank 0, then rtb_resolve_device there; gloo on CPU in the tests): the baseline the
+    fused kernel is measured against, and the fallback when peer mapping is unavailable.
 """
 from __future__ import annotations
 
@@ -72,3 +77,124 @@ def combine(accum, part: Partition, group=None, dst: int = 0, fix_w: bool = True
     if fix_w and part.rank == dst:
         accum[:, 3] = float(part.total_samples)
     return accum
+
+
+class _DeviceArray:
+    """Zero-copy view descriptor (``__cuda_array_interface__``) of a library-owned device buffer."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerExchange:
+    """Per-rank accumulation buffers mapped into every rank + the fused exchange/resolve kernel.
+
+    Mirrors what the reference gets for free from shared memory: its 8 threads write strips of ONE
+    `SharedStateImageWriter` buffer (src/camera.zig:22-27, src/main.zig:318-323).  Here every rank owns a full-frame
+    float4 buffer allocated by the library (cudaMalloc, so it can be exported), all ranks map all buffers, and after
+    the render each rank combines + resolves its slice of the frame into rank `root`'s buffers in one kernel.
+
+    group: a torch.distributed process group (None = default).  With the NCCL backend the barrier is a 1-element
+    all-reduce on the current CUDA stream (stream-ordered, no host synchronisation); with gloo (tests) it is a
+    device synchronise + host barrier.
+    """
+
+    def __init__(self, n_pixels: int, rank: int, world: int, device: int, group=None, root: int = 0):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _ffi, _check
+
+        self._ffi, self._check, self._C = _ffi, _check, C
+        self.n_pixels, self.rank, self.world, self.device, self.group, self.root = n_pixels, rank, world, device, group, root
+        lib = _ffi.rtb()
+        self._own = []
+        self._opened = []
+
+        def alloc(nbytes):
+            p = C.c_void_p()
+            _check(lib.rtb_buffer_alloc(device, nbytes, C.byref(p)), "rtb_buffer_alloc")
+            self._own.append(p.value)
+            return p.value
+
+        self.accum_ptr = alloc(n_pixels * 16)
+        self.rgba_ptr = alloc(n_pixels * 4)
+        self.accum = torch.as_tensor(_DeviceArray(self.accum_ptr, (n_pixels, 4), "<f4"), device=f"cuda:{device}")
+        self.rgba = torch.as_tensor(_DeviceArray(self.rgba_ptr, (n_pixels, 4), "|u1"), device=f"cuda:{device}")
+        self.accum.zero_()
+        self.rgba.zero_()
+        self.peer_accum = [None] * world
+        self.peer_accum[rank] = self.accum_ptr
+        self.root_accum, self.root_rgba = self.accum_ptr, self.rgba_ptr
+        self._nccl = world > 1 and dist.get_backend(group) == "nccl"
+        self._flag = torch.zeros(1, device=f"cuda:{device}") if self._nccl else None
+        if world > 1:
+            mine = []
+            for ptr in (self.accum_ptr, self.rgba_ptr):
+                h = _ffi.RtbIpcHandle()
+                _check(lib.rtb_ipc_export(device, ptr, C.byref(h)), "rtb_ipc_export")
+                mine.append(bytes(h.bytes))
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine, group=group)
+
+            def open_(raw):
+                h = _ffi.RtbIpcHandle()
+                C.memmove(h.bytes, raw, 64)
+                p = C.c_void_p()
+                _check(lib.rtb_ipc_open(device, C.byref(h), C.byref(p)), "rtb_ipc_open")
+                self._opened.append(p.value)
+                return p.value
+
+            for r in range(world):
+                if r != rank:
+                    self.peer_accum[r] = open_(everyone[r][0])
+            if rank != root:
+                self.root_accum = self.peer_accum[root]
+                self.root_rgba = open_(everyone[root][1])
+            self.barrier()
+        self._peers = (C.c_void_p * world)(*self.peer_accum)
+
+    def slice(self):
+        C = self._C
+        b, e = C.c_uint64(), C.c_uint64()
+        self._check(self._ffi.rtb().rtb_exchange_slice(self.n_pixels, self.world, self.rank, C.byref(b), C.byref(e)),
+                    "rtb_exchange_slice")
+        return b.value, e.value
+
+    def barrier(self):
+        """Orders the CUDA work of all ranks: nothing queued after it starts before everything queued before it, on
+        every rank, has finished."""
+        if self.world == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        if self._nccl:
+            dist.all_reduce(self._flag, group=self.group)
+        else:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+
+    def exchange(self, samples_per_pixel: float, stream: int = 0):
+        """barrier -> rtb_exchange_resolve on every rank -> barrier.  Afterwards rank `root`'s `accum` holds the
+        combined sums (.w = samples_per_pixel) and its `rgba` the resolved frame."""
+        self.barrier()
+        self._check(self._ffi.rtb().rtb_exchange_resolve(self._peers, self.world, self.rank, self.root_accum,
+                                                         self.root_rgba, self.n_pixels, float(samples_per_pixel),
+                                                         self.device, stream), "rtb_exchange_resolve")
+        self.barrier()
+
+    def close(self):
+        lib = self._ffi.rtb()
+        if self.world > 1:
+            try:
+                self.barrier()
+            except Exception:
+                pass
+        self.accum = self.rgba = None
+        for p in self._opened:
+            lib.rtb_ipc_close(self.device, p)
+        self._opened = []
+        for p in self._own:
+            lib.rtb_buffer_free(self.device, p)
+        self._own = []
