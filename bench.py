@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
+    ap.add_argument("--no-variants", action="store_true",
+                    help="skip the six integrator/traversal variant timings (keeps an ncu launch list to the headline path)")
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N>1 exchange step: p2p = fused reduce+resolve kernel over peer memory (rtb_exchange_resolve), "
                          "nccl = NCCL sum-reduce to rank 0 then rtb_resolve_device")
@@ -336,7 +338,7 @@ def run_ours(a):
 
     # -- the other variants, one untimed-for-the-headline step each (evidence for the choice; device-resident) ----
     variants = {}
-    for vname, vint, vtrav in (("megakernel/reference", p.RTB_INTEGRATOR_MEGAKERNEL, p.RTB_TRAVERSAL_REFERENCE),
+    for vname, vint, vtrav in () if a.no_variants else (("megakernel/reference", p.RTB_INTEGRATOR_MEGAKERNEL, p.RTB_TRAVERSAL_REFERENCE),
                                ("megakernel/ordered", p.RTB_INTEGRATOR_MEGAKERNEL, p.RTB_TRAVERSAL_ORDERED),
                                ("megakernel/sah", p.RTB_INTEGRATOR_MEGAKERNEL, p.RTB_TRAVERSAL_SAH),
                                ("wavefront/reference", p.RTB_INTEGRATOR_WAVEFRONT, p.RTB_TRAVERSAL_REFERENCE),
