@@ -412,7 +412,11 @@ def run_ours(a):
         "bound": "fp32", "kernel": "render_megakernel" if integ_name == "megakernel" else "wf_raygen+wf_extend+wf_shade+wf_accumulate",
         "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
         "peak_source": "FFMA microbenchmark measured in this run (FMA = 2 flops); the kernels run unfused, ceiling = peak/2",
-        "traffic": None,
+        # DRAM bytes of one step, from the ncu capture in profiles/r1g_dram_summary.csv (dram__bytes_read+write summed
+        # over every wavefront kernel of a render = 692.4 B per path on this workload; the megakernel moves ~16 B per
+        # path): queue/state traffic, not the "algorithmic bytes" (node/sphere fetches), which shared memory serves.
+        "traffic": (692.4 if integ_name == "wavefront" else 16.0) * paths_per_launch_group,
+        "traffic_source": "profiles/r1g_dram_summary.csv (ncu, per path, scaled to the step)",
         "algorithmic_flops_per_path": flops_per_path, "kernel_ms_per_step": kernel_ms,
         "counting": "achieved = flops of the REFERENCE traversal (left-then-right over the host's tree, SURVEY 8d) "
                     "/ kernel time; achieved_actual = flops of the traversal that ran",

@@ -113,7 +113,10 @@ int rtw_camera_init(const RtwCameraOptions* options, RtbCamera* camera_out); /* 
 int rtw_camera_render(RtbScene* scene, const RtwCameraOptions* options, const RtbRenderOptions* render_options,
                       int scrub, float* buffer, uint8_t* texture_buffer, RtbRenderStats* stats);
 
+/* Output formats ("save to file" is an open TODO of the reference, src/main.zig:47):
+ * P3 PPM as src/stdout.zig:5-18 prints it (values come from the RGBA8 buffer, so never 256), and an 8-bit RGB PNG. */
 int rtw_write_ppm(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height);
+int rtw_write_png(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height);
 
 #ifdef __cplusplus
 }

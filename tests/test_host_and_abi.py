@@ -199,6 +199,32 @@ def test_write_ppm(pkg, tmp_path):
     assert lines[:3] == ["P3", "3 2", "255"] and lines[3] == "255 0 1" and lines[8] == "14 15 16"   # stdout.zig:8
 
 
+def test_write_png(pkg, tmp_path):
+    """Decode the file with nothing but the PNG spec: signature, chunk CRCs, IHDR, zlib-inflate IDAT, filter 0."""
+    import struct
+    import zlib
+    rng = np.random.default_rng(4)
+    for w, h in ((3, 2), (257, 130)):      # the larger one needs more than one 65 535-byte stored block
+        rgba = rng.integers(0, 256, (h * w, 4)).astype(np.uint8)
+        path = str(tmp_path / f"o{w}.png")
+        pkg.write_png(path, rgba, w, h)
+        blob = open(path, "rb").read()
+        assert blob[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, chunks = 8, []
+        while pos < len(blob):
+            n, kind = struct.unpack(">I4s", blob[pos:pos + 8])
+            data = blob[pos + 8:pos + 8 + n]
+            (crc,) = struct.unpack(">I", blob[pos + 8 + n:pos + 12 + n])
+            assert crc == zlib.crc32(kind + data)
+            chunks.append((kind, data))
+            pos += 12 + n
+        assert [k for k, _ in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+        assert struct.unpack(">IIBBBBB", chunks[0][1]) == (w, h, 8, 2, 0, 0, 0)
+        raw = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(h, 1 + 3 * w)
+        assert (raw[:, 0] == 0).all()
+        assert np.array_equal(raw[:, 1:].reshape(h * w, 3), rgba[:, :3])
+
+
 # ---- the C-ABI libraries ------------------------------------------------------------------------------------------
 def _declared(header, prefix):
     text = open(os.path.join(ROOT, "include", header)).read()

@@ -326,6 +326,12 @@ def write_ppm(path: str, rgba: np.ndarray, width: int, height: int) -> None:
     _check(_ffi.rtw().rtw_write_ppm(path.encode(), rgba.ctypes.data, width, height), "rtw_write_ppm")
 
 
+def write_png(path: str, rgba: np.ndarray, width: int, height: int) -> None:
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    assert rgba.size == 4 * width * height
+    _check(_ffi.rtw().rtw_write_png(path.encode(), rgba.ctypes.data, width, height), "rtw_write_png")
+
+
 # BASELINE.json configs: camera + world factory per named scene.
 def book1_camera(width=1200, spp=500, max_depth=50):
     """Book-1 final scene camera = the reference's Camera defaults (src/camera.zig:70-91) with the legacy sky."""

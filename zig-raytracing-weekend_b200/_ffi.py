@@ -142,7 +142,7 @@ RTW_SYMBOLS = [
     "rtw_world_create", "rtw_world_new", "rtw_world_add_image", "rtw_world_add_sphere", "rtw_world_add_quad",
     "rtw_world_add_box", "rtw_world_add_medium",
     "rtw_world_build", "rtw_world_desc", "rtw_world_object_box", "rtw_world_destroy", "rtw_camera_defaults",
-    "rtw_camera_init", "rtw_camera_render", "rtw_write_ppm",
+    "rtw_camera_init", "rtw_camera_render", "rtw_write_ppm", "rtw_write_png",
 ]
 
 _rtb = None
@@ -230,5 +230,6 @@ def rtw() -> C.CDLL:
     lib.rtw_camera_render.argtypes = [vp, C.POINTER(RtwCameraOptions), C.POINTER(RtbRenderOptions), C.c_int, vp, vp,
                                       C.POINTER(RtbRenderStats)]
     lib.rtw_write_ppm.argtypes = [C.c_char_p, vp, u32, u32]
+    lib.rtw_write_png.argtypes = [C.c_char_p, vp, u32, u32]
     _rtw = lib
     return lib

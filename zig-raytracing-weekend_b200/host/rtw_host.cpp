@@ -727,4 +727,87 @@ bool writePpm(const std::string& path, const uint8_t* rgba, uint32_t width, uint
     return std::fclose(f) == 0;
 }
 
+// 8-bit RGB PNG from the RGBA8 texture buffer ("save to file" is an open TODO of the reference, src/main.zig:47).
+// Self-contained: stored (uncompressed) deflate blocks inside a zlib stream, CRC-32 per chunk, Adler-32 of the raw
+// scanlines — every PNG reader accepts it, and the file is byte-for-byte reproducible.
+namespace {
+uint32_t crc32Update(uint32_t crc, const uint8_t* data, size_t n) {
+    static uint32_t table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        ready = true;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ data[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+}
+void putBe32(std::vector<uint8_t>& v, uint32_t x) {
+    v.push_back((uint8_t)(x >> 24));
+    v.push_back((uint8_t)(x >> 16));
+    v.push_back((uint8_t)(x >> 8));
+    v.push_back((uint8_t)x);
+}
+bool writeChunk(FILE* f, const char type[4], const std::vector<uint8_t>& data) {
+    std::vector<uint8_t> head;
+    putBe32(head, (uint32_t)data.size());
+    head.insert(head.end(), type, type + 4);
+    uint32_t crc = crc32Update(0xffffffffu, head.data() + 4, 4);
+    crc = crc32Update(crc, data.data(), data.size()) ^ 0xffffffffu;
+    std::vector<uint8_t> tail;
+    putBe32(tail, crc);
+    return std::fwrite(head.data(), 1, head.size(), f) == head.size() &&
+           (data.empty() || std::fwrite(data.data(), 1, data.size(), f) == data.size()) &&
+           std::fwrite(tail.data(), 1, 4, f) == 4;
+}
+}  // namespace
+
+bool writePng(const std::string& path, const uint8_t* rgba, uint32_t width, uint32_t height) {
+    if (width == 0 || height == 0) return false;
+    // raw image data: per scanline a filter byte (0 = none) + RGB triples
+    std::vector<uint8_t> raw;
+    raw.reserve((size_t)height * (1 + 3 * (size_t)width));
+    for (uint32_t y = 0; y < height; ++y) {
+        raw.push_back(0);
+        for (uint32_t x = 0; x < width; ++x) {
+            const uint8_t* p = rgba + 4 * ((size_t)y * width + x);
+            raw.insert(raw.end(), p, p + 3);
+        }
+    }
+    std::vector<uint8_t> z;
+    z.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+    z.push_back(0x78);  // zlib header: deflate, 32 K window, no preset dictionary, check bits
+    z.push_back(0x01);
+    uint32_t a = 1, b = 0;  // Adler-32
+    for (size_t off = 0; off < raw.size();) {
+        const size_t n = std::min<size_t>(65535, raw.size() - off);
+        z.push_back(off + n == raw.size() ? 1 : 0);  // BFINAL, BTYPE = 00 (stored)
+        z.push_back((uint8_t)(n & 0xff));
+        z.push_back((uint8_t)(n >> 8));
+        z.push_back((uint8_t)(~n & 0xff));
+        z.push_back((uint8_t)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + (ptrdiff_t)off, raw.begin() + (ptrdiff_t)(off + n));
+        for (size_t i = off; i < off + n; ++i) {
+            a = (a + raw[i]) % 65521u;
+            b = (b + a) % 65521u;
+        }
+        off += n;
+    }
+    putBe32(z, (b << 16) | a);
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    static const uint8_t signature[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    bool ok = std::fwrite(signature, 1, 8, f) == 8;
+    std::vector<uint8_t> ihdr;
+    putBe32(ihdr, width);
+    putBe32(ihdr, height);
+    const uint8_t rest[5] = {8, 2, 0, 0, 0};  // bit depth 8, colour type 2 (RGB), deflate, adaptive filtering, no interlace
+    ihdr.insert(ihdr.end(), rest, rest + 5);
+    ok = ok && writeChunk(f, "IHDR", ihdr) && writeChunk(f, "IDAT", z) && writeChunk(f, "IEND", {});
+    return (std::fclose(f) == 0) && ok;
+}
+
 }  // namespace rtw

@@ -255,5 +255,7 @@ World randomSpheresWorld(HostRng& scene_rng, HostRng& bvh_rng, uint32_t n);
 
 // P3 PPM like src/stdout.zig:5-18 but from the RGBA8 texture buffer (values already <= 255).
 bool writePpm(const std::string& path, const uint8_t* rgba, uint32_t width, uint32_t height);
+// 8-bit RGB PNG of the same buffer (stored deflate blocks; no third-party encoder).
+bool writePng(const std::string& path, const uint8_t* rgba, uint32_t width, uint32_t height);
 
 }  // namespace rtw

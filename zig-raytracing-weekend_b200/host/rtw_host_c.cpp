@@ -282,3 +282,8 @@ extern "C" int rtw_write_ppm(const char* path, const uint8_t* rgba, uint32_t wid
     if (!path || !rgba) return RTB_ERR_INVALID_ARGUMENT;
     return writePpm(path, rgba, width, height) ? RTB_OK : RTB_ERR_INVALID_ARGUMENT;
 }
+
+extern "C" int rtw_write_png(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height) {
+    if (!path || !rgba) return RTB_ERR_INVALID_ARGUMENT;
+    return writePng(path, rgba, width, height) ? RTB_OK : RTB_ERR_INVALID_ARGUMENT;
+}
