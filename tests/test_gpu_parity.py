@@ -6,6 +6,7 @@ Bars (BASELINE.json north_star):
   * different seeds -> RMSE and mean bias within the oracle's own seed-to-seed spread.
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -13,6 +14,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REL = 1e-5  # stated tolerance for t / normal / uv (BASELINE.json)
 
 
@@ -481,3 +483,38 @@ def test_large_scene_global_memory_path(pkg, orc):
         diff = np.abs(s_acc[:, :3] - g_acc[:, :3]).max(axis=1)
         # ~0.25 % of the rays are undecidable in f32 from this camera (see above); a pixel holds ~4 of them
         assert np.count_nonzero(diff > 1e-4) <= 2e-2 * diff.shape[0]
+
+
+def test_wavefront_multi_pass_frames_and_tile_stats(pkg, book1, tmp_path):
+    """Frames with more pixels than one wavefront pass may hold are rendered as several passes over interleaved tile
+    subsets (RTB_WF_MAX_SLOTS forces that on a small frame; it is read once per process, hence the subprocess):
+    bit-identical to the megakernel.  Also: n_paths is exact under the tile partition."""
+    import subprocess
+    import sys
+    script = tmp_path / "multipass.py"
+    script.write_text(f"""
+import importlib, sys
+import numpy as np
+sys.path.insert(0, {ROOT!r})
+pkg = importlib.import_module("zig-raytracing-weekend_b200")
+world = pkg.World.book1()
+scene = pkg.Scene(world)
+cam = pkg.book1_camera(200, 6, 50).init()
+a, _, sa = scene.render(cam, pkg.render_options(seed=9, integrator=pkg.RTB_INTEGRATOR_WAVEFRONT))
+b, _, sb = scene.render(cam, pkg.render_options(seed=9, integrator=pkg.RTB_INTEGRATOR_MEGAKERNEL))
+assert np.array_equal(a, b), "multi-pass wavefront differs from the megakernel"
+assert sa["n_launches"] > 5 * (2 * 50 + 2), sa["n_launches"]          # really several passes
+print("ok", sa["n_launches"])
+""")
+    env = dict(os.environ, RTB_WF_MAX_SLOTS="4096")
+    out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+    world, scene = book1
+    cam = pkg.book1_camera(203, 2, 8).init()      # 203 x 114: ragged right and bottom tiles
+    total = 0
+    for rank in range(3):
+        o = pkg.render_options(seed=2, integrator=pkg.RTB_INTEGRATOR_MEGAKERNEL, tile_rank=rank, tile_world=3)
+        acc, _, st = scene.render(cam, o)
+        assert st["n_paths"] == 2 * np.count_nonzero(acc[:, 3] == 2.0)
+        total += st["n_paths"]
+    assert total == 2 * cam.image_width * cam.image_height

@@ -731,6 +731,27 @@ static int check_render_args(RtbScene* scene, const RtbCamera* cam, const RtbRen
     return RTB_OK;
 }
 
+// Pixels this call renders: the flat range [pixel_begin, +pixel_count) intersected with the 32x8 tiles t for which
+// t % tile_world == tile_rank.
+static uint64_t owned_pixels(const RtbCamera* cam, const RtbRenderOptions* opt) {
+    const uint64_t W = cam->image_width, H = cam->image_height;
+    const uint64_t lo = opt->pixel_begin;
+    const uint64_t hi = (opt->pixel_begin == 0 && opt->pixel_count == 0) ? W * H : lo + opt->pixel_count;
+    const uint64_t world = opt->tile_world ? opt->tile_world : 1u;
+    if (world == 1) return hi - lo;
+    const uint64_t tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+    uint64_t n = 0;
+    for (uint64_t t = opt->tile_rank; t < tiles_x * tiles_y; t += world) {
+        const uint64_t x0 = (t % tiles_x) * kTileW, y0 = (t / tiles_x) * kTileH;
+        const uint64_t x1 = x0 + kTileW < W ? x0 + kTileW : W, y1 = y0 + kTileH < H ? y0 + kTileH : H;
+        for (uint64_t y = y0; y < y1; ++y) {
+            const uint64_t a = y * W + x0 > lo ? y * W + x0 : lo, b = y * W + x1 < hi ? y * W + x1 : hi;
+            if (b > a) n += b - a;
+        }
+    }
+    return n;
+}
+
 // Core: enqueue the kernels for samples [begin, begin+count) on `stream`.  Caller holds the lock.
 static int render_enqueue(RtbScene* scene, const RtbCamera* cam, const RtbRenderOptions* opt, uint32_t begin,
                           uint32_t count, float* d_accum, cudaStream_t stream, LaunchInfo* info) {
@@ -770,10 +791,15 @@ static int render_device_locked(RtbScene* scene, const RtbCamera* cam, const Rtb
     const bool count_work = (opt->flags & RTB_FLAG_COUNT_WORK) != 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (stats) {
-        RTB_CUDA(cudaEventCreate(&ev0));
-        RTB_CUDA(cudaEventCreate(&ev1));
-        if (count_work) RTB_CUDA(cudaMemsetAsync(scene->d_counters, 0, 4 * sizeof(unsigned long long), stream));
-        RTB_CUDA(cudaEventRecord(ev0, stream));
+        cudaError_t e = cudaEventCreate(&ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&ev1);
+        if (e == cudaSuccess && count_work) e = cudaMemsetAsync(scene->d_counters, 0, 4 * sizeof(unsigned long long), stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev0, stream);
+        if (e != cudaSuccess) {
+            if (ev0) cudaEventDestroy(ev0);
+            if (ev1) cudaEventDestroy(ev1);
+            return cuda_fail(e, "render timers");
+        }
     }
     LaunchInfo info;
     int rc = RTB_OK;
@@ -791,9 +817,7 @@ static int render_device_locked(RtbScene* scene, const RtbCamera* cam, const Rtb
             std::memset(stats, 0, sizeof(*stats));
             stats->device_ms = ms;
             stats->n_launches = info.n_launches;
-            const uint32_t size = cam->image_width * cam->image_height;
-            const uint64_t npx = (opt->pixel_begin == 0 && opt->pixel_count == 0) ? size : opt->pixel_count;
-            stats->n_paths = npx * total;  // exact when tile_world <= 1
+            stats->n_paths = owned_pixels(cam, opt) * total;
             if (e == cudaSuccess && count_work) {
                 unsigned long long c[4];
                 e = cudaMemcpy(c, scene->d_counters, sizeof(c), cudaMemcpyDeviceToHost);

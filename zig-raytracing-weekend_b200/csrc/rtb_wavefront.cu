@@ -27,6 +27,8 @@
 
 #include <new>
 
+#include <cstdlib>
+
 namespace rtb {
 
 constexpr uint32_t kOctants = 8;
@@ -411,6 +413,18 @@ static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t
 // batch when run alone); on its own stream that tail overlaps the next batches' full-width bounces.
 // wf_accumulate calls are chained with events so every pixel still receives its samples in sample
 // order, i.e. the result stays bit-identical to the megakernel's and to a single-stream run.
+// Most path slots one pass may hold per sample (624 B each).  A frame with more owned pixels than this is rendered
+// in several passes over interleaved subsets of its tiles (every pixel belongs to exactly one pass, so the per-pixel
+// sample order is unchanged).  RTB_WF_MAX_SLOTS overrides it (tests force the multi-pass path on a small frame).
+static uint32_t wf_max_slots_per_sample() {
+    static const uint32_t v = [] {
+        const char* s = std::getenv("RTB_WF_MAX_SLOTS");
+        const unsigned long long x = s ? std::strtoull(s, nullptr, 10) : 0ull;
+        return (x >= 256ull && x <= 0x1fffffffull) ? (uint32_t)x : (48u << 20);
+    }();
+    return v;
+}
+
 cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool count_work, cudaStream_t stream,
                              LaunchInfo* info) {
     const uint32_t tiles_x = (p.cam.width + kTileW - 1u) / kTileW;
@@ -420,6 +434,19 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     if (p.tile_rank >= world) return cudaErrorInvalidValue;
     const uint32_t owned = (tiles > p.tile_rank) ? (tiles - p.tile_rank + world - 1u) / world : 0u;
     if (owned == 0u || p.sample_count == 0u) return cudaSuccess;
+    if ((uint64_t)owned * kCtaThreads > wf_max_slots_per_sample()) {
+        const uint64_t k64 = ((uint64_t)owned * kCtaThreads + wf_max_slots_per_sample() - 1u) / wf_max_slots_per_sample();
+        if (k64 * world > 0xffffffffull) return cudaErrorInvalidValue;
+        const uint32_t k = (uint32_t)k64;
+        for (uint32_t j = 0; j < k; ++j) {  // pass j owns the tiles t with t % (world * k) == tile_rank + j * world
+            RenderParams q = p;
+            q.tile_world = world * k;
+            q.tile_rank = p.tile_rank + j * world;
+            const cudaError_t ej = wavefront_render(st, q, count_work, stream, info);
+            if (ej != cudaSuccess) return ej;
+        }
+        return cudaSuccess;
+    }
     cudaError_t e = wf_init(st);
     if (e != cudaSuccess) return e;
     const uint32_t slots_per_sample = owned * kCtaThreads;
@@ -431,9 +458,14 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     if ((uint64_t)B * slots_per_sample > 0x1fffffffull) B = (uint32_t)(0x1fffffffull / slots_per_sample);
     if (B < 1u) return cudaErrorInvalidValue;
     const uint32_t n_batches = (p.sample_count + B - 1u) / B;
-    const int lanes_used = n_batches < (uint32_t)kLanes ? (int)n_batches : kLanes;
+    int lanes_used = n_batches < (uint32_t)kLanes ? (int)n_batches : kLanes;
     for (int l = 0; l < lanes_used; ++l) {
         e = lane_reserve(&st->lanes[l], (size_t)B * slots_per_sample);
+        if (e == cudaErrorMemoryAllocation && l > 0) {  // not enough memory for every lane: pipeline over fewer
+            (void)cudaGetLastError();
+            lanes_used = l;
+            break;
+        }
         if (e != cudaSuccess) return e;
     }
 
@@ -453,7 +485,7 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         const uint32_t s0 = batch * B;
         const uint32_t nb = (p.sample_count - s0 < B) ? p.sample_count - s0 : B;
         const uint32_t cap = nb * slots_per_sample;
-        const int lane_id = (int)(batch % (uint32_t)kLanes);
+        const int lane_id = (int)(batch % (uint32_t)lanes_used);
         WfLane& ln = st->lanes[lane_id];
         WfParams P{};
         P.R = p;
