@@ -50,9 +50,10 @@ def parse_args():
     ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
     ap.add_argument("--no-variants", action="store_true",
                     help="skip the six integrator/traversal variant timings (keeps an ncu launch list to the headline path)")
-    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
+    ap.add_argument("--exchange", choices=["auto", "p2p", "nccl"], default="auto",
                     help="N>1 exchange step: p2p = fused reduce+resolve kernel over peer memory (rtb_exchange_resolve), "
-                         "nccl = NCCL sum-reduce to rank 0 then rtb_resolve_device")
+                         "nccl = NCCL sum-reduce to rank 0 then rtb_resolve_device, auto = time both on this box and "
+                         "take the faster (measured: p2p at N=2, NCCL's in-switch reduction at N>=4)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank renders --spp samples (sample partition only); strong: the ranks share "
                          "--spp samples (samples) or the frame's tiles (tiles) — e.g. BASELINE config 5: "
@@ -215,24 +216,46 @@ def run_ours(a):
     sptr = stream.cuda_stream
 
     px = None
-    if world_size > 1 and a.exchange == "p2p":
+    if world_size > 1 and a.exchange != "nccl":
         # per-rank buffers owned by the library and mapped into every rank (CUDA IPC over NVLink/NVSwitch)
         px = mg.PeerExchange(npx, rank, world_size, local_rank)
         d_acc, d_rgba = px.accum, px.rgba
     else:
         d_acc = torch.zeros(npx, 4, device=dev, dtype=torch.float32)
         d_rgba = torch.zeros(npx, 4, device=dev, dtype=torch.uint8)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    exchange_kind = "p2p" if px is not None else "nccl"
 
-    def exchange_and_resolve(part):
+    def exchange_and_resolve(part, kind=None):
         """The exchange step + resolve: afterwards rank 0 holds the combined sums and the RGBA8 frame."""
-        if px is not None:
+        if (kind or exchange_kind) == "p2p":
             px.exchange(float(part.total_samples), sptr)
             return
         mg.combine(d_acc, part, fix_w=False)
         if rank == 0:
             p._check(p._ffi.rtb().rtb_resolve_device(d_acc.data_ptr(), d_rgba.data_ptr(), npx,
                                                      float(part.total_samples), local_rank, sptr), "rtb_resolve_device")
-    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+
+    exchange_probe = None
+    if world_size > 1 and a.exchange == "auto":   # measured, not assumed: both exchanges on this frame size, this box
+        part0 = mg.plan(a.partition, rank, world_size, a.spp, weak=(a.partition == "samples" and a.scaling == "weak"))
+        times = {}
+        for kind in ("p2p", "nccl"):
+            for _ in range(2):
+                exchange_and_resolve(part0, kind)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(stream)
+            for _ in range(5):
+                exchange_and_resolve(part0, kind)
+            x1.record(stream)
+            torch.cuda.synchronize(dev)
+            tk = torch.tensor([x0.elapsed_time(x1) / 5], device=dev, dtype=torch.float64)
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+            times[kind] = tk.item()
+        exchange_kind = "p2p" if times["p2p"] <= times["nccl"] else "nccl"
+        exchange_probe = {"p2p_ms": times["p2p"], "nccl_ms": times["nccl"]}
 
     traversal = {"reference": p.RTB_TRAVERSAL_REFERENCE, "ordered": p.RTB_TRAVERSAL_ORDERED,
                  "sah": p.RTB_TRAVERSAL_SAH}[a.traversal]
@@ -391,7 +414,7 @@ def run_ours(a):
         e2e = {"value": paths_per_step * a.steps / dt.item() / 1e6, "unit": "Mpaths/s",
                "h2d_bytes_per_step": 16 * npx, "d2h_bytes_per_step": 20 * npx,
                "api": "rtb_render (host buffers)" if world_size == 1 else
-                      ("H2D + rtb_render_device + rtb_exchange_resolve (peer memory) + D2H" if px is not None else
+                      ("H2D + rtb_render_device + rtb_exchange_resolve (peer memory) + D2H" if exchange_kind == "p2p" else
                        "H2D + rtb_render_device + NCCL reduce + rtb_resolve_device + D2H")}
 
     if px is not None:
@@ -460,8 +483,8 @@ def run_ours(a):
         "integrator_probe": probe, "variants_mpaths_per_s": variants,
         "exchange": None if world_size == 1 else {
             "kind": "rtb_exchange_resolve: fused reduce-scatter + resolve + gather over peer memory, one kernel per rank"
-                    if a.exchange == "p2p" else "NCCL reduce(sum) to rank 0 + rtb_resolve_device",
-            "ms_per_step": exchange_ms, "bytes_per_rank": 16 * npx},
+                    if exchange_kind == "p2p" else "NCCL reduce(sum) to rank 0 + rtb_resolve_device",
+            "ms_per_step": exchange_ms, "bytes_per_rank": 16 * npx, "probe": exchange_probe},
     }
     print(json.dumps(out))
     if world_size > 1:

@@ -342,8 +342,13 @@ int rtb_ipc_export(int device, const void* device_ptr, RtbIpcHandle* handle_out)
 int rtb_ipc_open(int device, const RtbIpcHandle* handle, void** device_ptr_out);
 int rtb_ipc_close(int device, void* device_ptr);
 
-/* Slice of the frame that rank `rank` of `world` combines: [*begin_out, *end_out), 256-pixel aligned. */
-int rtb_exchange_slice(uint64_t n_pixels, uint32_t world, uint32_t rank, uint64_t* begin_out, uint64_t* end_out);
+/* Slice of the frame that rank `rank` of `world` combines: [*begin_out, *end_out), 256-pixel aligned; the slices of
+ * ranks 0..world-1 tile [0, n_pixels) in rank order.  The ROOT's NVLink ingress is the bottleneck of the step (it
+ * receives every other rank's results on top of whatever it reads itself), so the split is not even: with world >= 3
+ * the root combines nothing and only receives; with world == 2 the root combines the whole frame (it then reads one
+ * remote buffer and receives nothing); world == 1 is a plain resolve. */
+int rtb_exchange_slice(uint64_t n_pixels, uint32_t world, uint32_t rank, uint32_t root, uint64_t* begin_out,
+                       uint64_t* end_out);
 
 /* Fused exchange + resolve.  peer_accum[r] = rank r's float4 accumulation buffer as mapped into this process
  * (peer_accum[rank] is this rank's own buffer).  For the pixels of this rank's slice: sum over r in rank order
@@ -352,9 +357,9 @@ int rtb_exchange_slice(uint64_t n_pixels, uint32_t world, uint32_t rank, uint64_
  * place).  Asynchronous on `cuda_stream`.  All ranks must have finished rendering before any rank's launch starts and
  * nobody may touch the buffers again before every rank's launch has finished: bracket it with a stream-ordered
  * barrier (e.g. a 1-element NCCL all-reduce on the same stream). */
-int rtb_exchange_resolve(const float* const* peer_accum, uint32_t world, uint32_t rank, float* root_accum_out,
-                         uint8_t* root_rgba_out, uint64_t n_pixels, float samples_per_pixel, int device,
-                         void* cuda_stream);
+int rtb_exchange_resolve(const float* const* peer_accum, uint32_t world, uint32_t rank, uint32_t root,
+                         float* root_accum_out, uint8_t* root_rgba_out, uint64_t n_pixels, float samples_per_pixel,
+                         int device, void* cuda_stream);
 
 /* Progressive / cancellable render, preserving the GUI behaviour of the reference (progress
  * polling: countSamples src/main.zig:470-477; STOP: stopRender :328-336; per-sample refresh of

@@ -190,8 +190,8 @@ def rtb() -> C.CDLL:
     lib.rtb_ipc_export.argtypes = [C.c_int, vp, C.POINTER(RtbIpcHandle)]
     lib.rtb_ipc_open.argtypes = [C.c_int, C.POINTER(RtbIpcHandle), C.POINTER(vp)]
     lib.rtb_ipc_close.argtypes = [C.c_int, vp]
-    lib.rtb_exchange_slice.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
-    lib.rtb_exchange_resolve.argtypes = [C.POINTER(vp), u32, u32, vp, vp, u64, f32, C.c_int, vp]
+    lib.rtb_exchange_slice.argtypes = [u64, u32, u32, u32, C.POINTER(u64), C.POINTER(u64)]
+    lib.rtb_exchange_resolve.argtypes = [C.POINTER(vp), u32, u32, u32, vp, vp, u64, f32, C.c_int, vp]
     for s in RTB_SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("rtb_abi_version", "rtb_last_error"):

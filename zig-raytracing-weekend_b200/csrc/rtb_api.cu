@@ -902,13 +902,22 @@ extern "C" int rtb_ipc_close(int device, void* device_ptr) {
     return RTB_OK;
 }
 
-extern "C" int rtb_exchange_slice(uint64_t n_pixels, uint32_t world, uint32_t rank, uint64_t* begin_out,
+extern "C" int rtb_exchange_slice(uint64_t n_pixels, uint32_t world, uint32_t rank, uint32_t root, uint64_t* begin_out,
                                   uint64_t* end_out) {
     if (!begin_out || !end_out) return fail(RTB_ERR_INVALID_ARGUMENT, "begin_out/end_out is NULL");
-    if (world == 0 || rank >= world) return fail(RTB_ERR_INVALID_ARGUMENT, "rank %u out of range (world %u)", rank, world);
-    uint64_t per = (n_pixels + world - 1) / world;
+    if (world == 0 || rank >= world || root >= world)
+        return fail(RTB_ERR_INVALID_ARGUMENT, "rank %u / root %u out of range (world %u)", rank, root, world);
+    // Which ranks combine (see rtb.h for the policy); k = number of combining ranks before this one.
+    auto works = [&](uint32_t r) { return world == 1 ? true : (world == 2 ? r == root : r != root); };
+    uint32_t workers = 0, k = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+        if (!works(r)) continue;
+        ++workers;
+        if (r < rank) ++k;
+    }
+    uint64_t per = (n_pixels + workers - 1) / workers;
     per = (per + 255u) / 256u * 256u;
-    uint64_t b = per * rank, e = per * (rank + 1ull);
+    uint64_t b = per * k, e = per * (k + (works(rank) ? 1ull : 0ull));
     if (b > n_pixels) b = n_pixels;
     if (e > n_pixels) e = n_pixels;
     *begin_out = b;
@@ -916,11 +925,12 @@ extern "C" int rtb_exchange_slice(uint64_t n_pixels, uint32_t world, uint32_t ra
     return RTB_OK;
 }
 
-extern "C" int rtb_exchange_resolve(const float* const* peer_accum, uint32_t world, uint32_t rank, float* root_accum_out,
-                                    uint8_t* root_rgba_out, uint64_t n_pixels, float samples_per_pixel, int device,
-                                    void* cuda_stream) {
-    if (world == 0 || world > kMaxPeers || rank >= world)
-        return fail(RTB_ERR_INVALID_ARGUMENT, "world %u / rank %u out of range (max %u ranks)", world, rank, kMaxPeers);
+extern "C" int rtb_exchange_resolve(const float* const* peer_accum, uint32_t world, uint32_t rank, uint32_t root,
+                                    float* root_accum_out, uint8_t* root_rgba_out, uint64_t n_pixels,
+                                    float samples_per_pixel, int device, void* cuda_stream) {
+    if (world == 0 || world > kMaxPeers || rank >= world || root >= world)
+        return fail(RTB_ERR_INVALID_ARGUMENT, "world %u / rank %u / root %u out of range (max %u ranks)", world, rank, root,
+                    kMaxPeers);
     if (!peer_accum || !root_accum_out || !root_rgba_out) return fail(RTB_ERR_INVALID_ARGUMENT, "NULL buffer");
     if (!(samples_per_pixel > 0.0f)) return fail(RTB_ERR_INVALID_ARGUMENT, "samples_per_pixel must be > 0");
     PeerAccums peers{};
@@ -929,7 +939,7 @@ extern "C" int rtb_exchange_resolve(const float* const* peer_accum, uint32_t wor
         peers.p[r] = reinterpret_cast<const float4*>(peer_accum[r]);
     }
     uint64_t begin = 0, end = 0;
-    const int rc = rtb_exchange_slice(n_pixels, world, rank, &begin, &end);
+    const int rc = rtb_exchange_slice(n_pixels, world, rank, root, &begin, &end);
     if (rc != RTB_OK) return rc;
     RTB_CUDA(cudaSetDevice(device));
     const cudaError_t e = launch_exchange_resolve(peers, world, reinterpret_cast<float4*>(root_accum_out),

@@ -5,6 +5,8 @@
 //   K4 resolve_kernel    : toGamma2 + RGBA8 quantise                    (src/color.zig:43-62)
 #include "rtb_kernels.cuh"
 
+#include <cstdlib>
+
 namespace rtb {
 
 // ------------------------------------------------------------------------------------------
@@ -268,52 +270,86 @@ cudaError_t launch_resolve(const float4* d_accum, uchar4* d_rgba, uint64_t n_pix
 // gather in one pass: every byte crosses NVLink once, no GPU receives more than (world-1)/world of a frame, and the
 // resolve costs no extra trip through HBM.  The caller brackets the launch with a stream-ordered barrier.
 // ------------------------------------------------------------------------------------------
-template <int WORLD>
+template <int WORLD, int PPT>
 __global__ void __launch_bounds__(256) exchange_resolve_kernel(const PeerAccums peers, uint32_t world,
                                                                float4* root_accum,  // may alias peers.p[root]
                                                                uchar4* __restrict__ root_rgba, uint64_t begin,
                                                                uint64_t end, float samples_per_pixel) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
-        float4 v[WORLD > 0 ? WORLD : 1];
-        float4 s;
+    // PPT pixels per thread and iteration, 256 apart (coalesced), all WORLD * PPT loads issued before the first add:
+    // the remote ones have NVLink latency, so bytes in flight are what sets the rate.
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * PPT;
+    for (uint64_t i0 = begin + (uint64_t)blockIdx.x * blockDim.x * PPT + threadIdx.x; i0 < end; i0 += stride) {
+        float4 v[WORLD > 0 ? WORLD : 1][PPT];
+        float4 s[PPT];
         if (WORLD > 0) {
 #pragma unroll
-            for (int r = 0; r < WORLD; ++r) v[r] = peers.p[r][i];  // all loads in flight before the first add
-            s = v[0];
+            for (int r = 0; r < WORLD; ++r)
 #pragma unroll
-            for (int r = 1; r < WORLD; ++r) {
-                s.x += v[r].x;
-                s.y += v[r].y;
-                s.z += v[r].z;
+                for (int k = 0; k < PPT; ++k) {
+                    const uint64_t i = i0 + (uint64_t)k * 256u;
+                    v[r][k] = i < end ? peers.p[r][i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                s[k] = v[0][k];
+#pragma unroll
+                for (int r = 1; r < WORLD; ++r) {
+                    s[k].x += v[r][k].x;
+                    s[k].y += v[r][k].y;
+                    s[k].z += v[r][k].z;
+                }
             }
         } else {
-            s = peers.p[0][i];
-            for (uint32_t r = 1; r < world; ++r) {
-                const float4 t = peers.p[r][i];
-                s.x += t.x;
-                s.y += t.y;
-                s.z += t.z;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const uint64_t i = i0 + (uint64_t)k * 256u;
+                s[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < end) {
+                    s[k] = peers.p[0][i];
+                    for (uint32_t r = 1; r < world; ++r) {
+                        const float4 t = peers.p[r][i];
+                        s[k].x += t.x;
+                        s[k].y += t.y;
+                        s[k].z += t.z;
+                    }
+                }
             }
         }
-        s.w = samples_per_pixel;
-        root_accum[i] = s;
-        root_rgba[i] = quantise(s, samples_per_pixel);
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const uint64_t i = i0 + (uint64_t)k * 256u;
+            if (i < end) {
+                s[k].w = samples_per_pixel;
+                root_accum[i] = s[k];
+                root_rgba[i] = quantise(s[k], samples_per_pixel);
+            }
+        }
+    }
+}
+
+template <int PPT>
+static void exchange_dispatch(const PeerAccums& peers, uint32_t world, float4* root_accum, uchar4* root_rgba,
+                              uint64_t begin, uint64_t end, float spp, uint32_t g, cudaStream_t stream) {
+    switch (world) {
+        case 2: exchange_resolve_kernel<2, PPT><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, spp); break;
+        case 4: exchange_resolve_kernel<4, PPT><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, spp); break;
+        case 8: exchange_resolve_kernel<8, PPT><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, spp); break;
+        default: exchange_resolve_kernel<0, PPT><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, spp); break;
     }
 }
 
 cudaError_t launch_exchange_resolve(const PeerAccums& peers, uint32_t world, float4* root_accum, uchar4* root_rgba,
                                     uint64_t begin, uint64_t end, float samples_per_pixel, cudaStream_t stream) {
     if (end <= begin) return cudaSuccess;
-    uint64_t blocks = (end - begin + 255u) / 256u;
-    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    static const int ppt = [] { const char* s = std::getenv("RTB_XCHG_PPT"); return s ? std::atoi(s) : 1; }();
+    static const int bps = [] { const char* s = std::getenv("RTB_XCHG_BLOCKS_PER_SM"); return s ? std::atoi(s) : 8; }();
+    const int p = ppt == 4 ? 4 : (ppt == 2 ? 2 : 1);
+    uint64_t blocks = (end - begin + 256u * p - 1u) / (256u * p);
+    if (blocks > 148u * (uint64_t)(bps > 0 ? bps : 8)) blocks = 148u * (uint64_t)(bps > 0 ? bps : 8);
     const uint32_t g = (uint32_t)blocks;
-    switch (world) {
-        case 2: exchange_resolve_kernel<2><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel); break;
-        case 4: exchange_resolve_kernel<4><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel); break;
-        case 8: exchange_resolve_kernel<8><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel); break;
-        default: exchange_resolve_kernel<0><<<g, 256, 0, stream>>>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel); break;
-    }
+    if (p == 4) exchange_dispatch<4>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel, g, stream);
+    else if (p == 2) exchange_dispatch<2>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel, g, stream);
+    else exchange_dispatch<1>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel, g, stream);
     return cudaGetLastError();
 }
 

@@ -158,7 +158,8 @@ class PeerExchange:
     def slice(self):
         C = self._C
         b, e = C.c_uint64(), C.c_uint64()
-        self._check(self._ffi.rtb().rtb_exchange_slice(self.n_pixels, self.world, self.rank, C.byref(b), C.byref(e)),
+        self._check(self._ffi.rtb().rtb_exchange_slice(self.n_pixels, self.world, self.rank, self.root, C.byref(b),
+                                                       C.byref(e)),
                     "rtb_exchange_slice")
         return b.value, e.value
 
@@ -179,7 +180,7 @@ class PeerExchange:
         """barrier -> rtb_exchange_resolve on every rank -> barrier.  Afterwards rank `root`'s `accum` holds the
         combined sums (.w = samples_per_pixel) and its `rgba` the resolved frame."""
         self.barrier()
-        self._check(self._ffi.rtb().rtb_exchange_resolve(self._peers, self.world, self.rank, self.root_accum,
+        self._check(self._ffi.rtb().rtb_exchange_resolve(self._peers, self.world, self.rank, self.root, self.root_accum,
                                                          self.root_rgba, self.n_pixels, float(samples_per_pixel),
                                                          self.device, stream), "rtb_exchange_resolve")
         self.barrier()
