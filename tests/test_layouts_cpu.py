@@ -26,8 +26,9 @@ def test_layout_invariants(pkg, scene, earthmap):
     for mode in (0, 1, 2):
         for octant in range(8):
             L, n = _layout(pkg, world, mode, octant)
-            # modes 0/1: the host's 2k-1 nodes; mode 2 (SAH) puts a box node in front of each of the k leaves
-            assert n == (d.n_nodes if mode < 2 else d.n_nodes + (d.n_nodes + 1) // 2)
+            # modes 0/1: the host's 2k-1 nodes; mode 2 (SAH) puts a box node in front of each of the k leaves and
+            # does not emit the root's own box (the walk starts with the root's two subtrees)
+            assert n == (d.n_nodes if mode < 2 else d.n_nodes + (d.n_nodes + 1) // 2 - 1)
             meta = L[:, 3].view(np.uint32)
             assert meta[n] == END                                       # the sentinel closes every octant
             kind, idx = meta[:n] >> 30, meta[:n] & 0x3FFFFFFF

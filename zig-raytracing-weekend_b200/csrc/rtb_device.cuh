@@ -64,7 +64,7 @@ struct DevScene {
     // Each octant's array holds oct_n_nodes[mode] + 1 entries: the last one is the end sentinel (RTB_META_END).
     // Modes 0 and 1 have the host tree's n_nodes entries; mode 2 additionally puts a BOX node (the object's
     // own bounding box, skip = past the leaf) in front of every leaf, so a leaf is only tested when the ray
-    // enters its box: 3n - 1 entries for n objects.
+    // enters its box, and the root's own box is not emitted (the walk starts with its two subtrees): 3n - 2 entries for n objects.
     const float4* oct_nodes[3];
     uint32_t oct_n_nodes[3];
     // 4 per object: the leaf record {center1, kind|object}, {center_vec, radius} and the object's material
