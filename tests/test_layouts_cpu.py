@@ -26,9 +26,16 @@ def test_layout_invariants(pkg, scene, earthmap):
     for mode in (0, 1, 2):
         for octant in range(8):
             L, n = _layout(pkg, world, mode, octant)
-            # modes 0/1: the host's 2k-1 nodes; mode 2 (SAH) puts a box node in front of each of the k leaves and
-            # does not emit the root's own box (the walk starts with the root's two subtrees)
-            assert n == (d.n_nodes if mode < 2 else d.n_nodes + (d.n_nodes + 1) // 2 - 1)
+            meta_all = L[:, 3].view(np.uint32)
+            # mode 2 (SAH) starts with the "huge" objects (box >= half of the scene's: the ground sphere) as plain leaves
+            huge = 0
+            while mode == 2 and huge < n and meta_all[huge] >= (1 << 30):
+                huge += 1
+            rest = d.n_hittables - huge
+            # modes 0/1: the host's 2k-1 nodes; mode 2: the huge leaves, then the tree of the rest with a box node in
+            # front of each leaf and without the root's own box (the walk starts with the root's two subtrees)
+            assert n == (d.n_nodes if mode < 2 else huge + 3 * rest - (2 if rest > 1 else 1))
+            assert huge == ({"book1": 1}.get(scene, 0) if mode == 2 else 0)   # the r = 1000 ground sphere
             meta = L[:, 3].view(np.uint32)
             assert meta[n] == END                                       # the sentinel closes every octant
             kind, idx = meta[:n] >> 30, meta[:n] & 0x3FFFFFFF
@@ -39,14 +46,15 @@ def test_layout_invariants(pkg, scene, earthmap):
                 assert (idx[inner] > inner + 2).all() and (idx[inner] <= n).all()   # skip jumps over >= 2 children
             else:
                 leaf_box = inner[idx[inner] == inner + 2]          # {object box, skip past the leaf}, {leaf}
-                assert leaves[leaf_box + 1].all() and len(leaf_box) == d.n_hittables
+                assert leaves[leaf_box + 1].all() and len(leaf_box) == rest
                 assert (idx[inner] >= inner + 2).all() and (idx[inner] <= n).all()
                 # the leaf's box is the host's box for that object, padded outwards by <= 2^-20 of the scene extent
                 obj = idx[leaf_box + 1]
                 host = np.array([world.object_box(int(k)) for k in obj], np.float32)
                 lo = np.minimum(L[leaf_box, :3], L[leaf_box, 4:7])
                 hi = np.maximum(L[leaf_box, :3], L[leaf_box, 4:7])
-                extent = np.abs(host).reshape(-1, 2, 3).max(axis=(0, 1))
+                everything = np.array([world.object_box(k) for k in range(d.n_hittables)], np.float32)
+                extent = np.abs(everything).reshape(-1, 2, 3).max(axis=(0, 1))   # of the whole scene, huge objects too
                 assert (lo <= host[:, :3]).all() and (hi >= host[:, 3:]).all()
                 assert (host[:, :3] - lo <= extent * 2.0 ** -20).all() and (hi - host[:, 3:] <= extent * 2.0 ** -20).all()
             # pre-swapped slabs: entry plane = max where the octant bit is set, min otherwise

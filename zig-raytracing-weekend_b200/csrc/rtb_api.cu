@@ -281,14 +281,14 @@ static bool child_order_swapped(const RtbSceneDesc* d, const RtbBvhNode& nd, int
 }
 
 static void emit_layout(const RtbSceneDesc* d, const std::vector<uint32_t>& size, const std::vector<uint32_t>& quad_slot,
-                        int octant, bool ordered, float4* out, bool box_leaves = false) {
+                        int octant, bool ordered, float4* out, bool box_leaves = false, uint32_t slot_base = 0u) {
     if (d->n_nodes == 0) return;
     struct Item {
         int32_t node;
         uint32_t slot;
     };
     std::vector<Item> work;
-    work.push_back({d->root, 0u});
+    work.push_back({d->root, slot_base});
     if (box_leaves && d->nodes[d->root].leaf < 0) {
         // The root's box test is wasted work (its children's boxes lie inside it and nearly every ray enters it):
         // the SAH layouts start with the root's two subtrees, one slot less.
@@ -299,8 +299,8 @@ static void emit_layout(const RtbSceneDesc* d, const std::vector<uint32_t>& size
             first = nd.right;
             second = nd.left;
         }
-        work.push_back({second, layout_slots(size[first], true)});
-        work.push_back({first, 0u});
+        work.push_back({second, slot_base + layout_slots(size[first], true)});
+        work.push_back({first, slot_base});
     }
     while (!work.empty()) {
         const Item it = work.back();
@@ -338,7 +338,12 @@ static void emit_layout(const RtbSceneDesc* d, const std::vector<uint32_t>& size
 // splits at the median (src/bvh.zig:48-67), which on Book-1 costs 50 slab tests per ray and on the
 // 1 M-sphere scene 774; this tree only changes WHICH nodes are visited — slab test, sphere test and
 // every hit value are computed by the same code.  One object per leaf, so it has the same 2n-1 nodes.
-static int32_t build_sah(const RtbSceneDesc* d, const std::vector<uint32_t>& reachable, std::vector<RtbBvhNode>& out) {
+// Objects whose box covers at least half of the scene's (the r = 1000 ground sphere of the book scenes) are kept out
+// of the tree: `huge` lists them, the layouts test them first, as plain leaves without a box test — every lane of a
+// warp does that at the same time (no divergence), their box would be entered by nearly every ray anyway, and the hit
+// they usually produce prunes the walk that follows.
+static int32_t build_sah(const RtbSceneDesc* d, const std::vector<uint32_t>& reachable, std::vector<RtbBvhNode>& out,
+                         std::vector<int32_t>& huge) {
     struct Item {
         float bmin[3], bmax[3], c[3];
         int32_t object;
@@ -372,6 +377,30 @@ static int32_t build_sah(const RtbSceneDesc* d, const std::vector<uint32_t>& rea
                 it.bmax[a] += pad;
             }
     }
+    huge.clear();
+    auto area = [](const float* mn, const float* mx) {
+        const double x = (double)mx[0] - mn[0], y = (double)mx[1] - mn[1], z = (double)mx[2] - mn[2];
+        return x * y + y * z + z * x;
+    };
+#ifndef RTB_SAH_HUGE_FIRST
+#define RTB_SAH_HUGE_FIRST 1
+#endif
+    if (RTB_SAH_HUGE_FIRST && items.size() > 8) {
+        float wmn[3] = {INFINITY, INFINITY, INFINITY}, wmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (const Item& it : items)
+            for (int a = 0; a < 3; ++a) {
+                wmn[a] = std::fmin(wmn[a], it.bmin[a]);
+                wmx[a] = std::fmax(wmx[a], it.bmax[a]);
+            }
+        const double whole = area(wmn, wmx);
+        std::vector<Item> rest;
+        rest.reserve(items.size());
+        for (const Item& it : items) {
+            if (huge.size() < 4 && area(it.bmin, it.bmax) >= 0.5 * whole) huge.push_back(it.object);
+            else rest.push_back(it);
+        }
+        items.swap(rest);
+    }
     out.clear();
     if (items.empty()) return -1;
     out.reserve(2 * items.size());
@@ -382,10 +411,6 @@ static int32_t build_sah(const RtbSceneDesc* d, const std::vector<uint32_t>& rea
     };
     constexpr int kBins = 32;  // measured on Book-1: 16 bins 26.2 slab tests per ray, 32: 25.6, 64 or an exact sweep: 25.7
     constexpr int kMaxBins = kBins;
-    auto area = [](const float* mn, const float* mx) {
-        const double x = (double)mx[0] - mn[0], y = (double)mx[1] - mn[1], z = (double)mx[2] - mn[2];
-        return x * y + y * z + z * x;
-    };
     std::vector<Task> stack;
     stack.push_back({0u, (uint32_t)items.size(), -1, false});
     while (!stack.empty()) {
@@ -490,6 +515,35 @@ static int32_t build_sah(const RtbSceneDesc* d, const std::vector<uint32_t>& rea
     return 0;
 }
 
+// The RTB_TRAVERSAL_SAH layout of one octant: the huge objects as leading leaves, then the tree of the rest (boxed
+// leaves, no root box).  SahTree is built once per scene.
+struct SahTree {
+    std::vector<RtbBvhNode> nodes;
+    std::vector<uint32_t> size;
+    std::vector<int32_t> huge;
+    RtbSceneDesc desc{};
+    uint32_t layout_nodes = 0;  // entries per octant, without the end sentinel
+};
+static int sah_tree_build(const RtbSceneDesc* desc, const std::vector<uint32_t>& reachable, SahTree& t) {
+    t.desc = *desc;
+    t.desc.root = build_sah(desc, reachable, t.nodes, t.huge);
+    t.desc.nodes = t.nodes.data();
+    t.desc.n_nodes = (uint32_t)t.nodes.size();
+    uint32_t depth = 0;
+    if (t.desc.n_nodes) {
+        const int rc = tree_sizes(&t.desc, t.size, &depth);
+        if (rc != RTB_OK) return rc;
+    }
+    const uint32_t rest = t.desc.n_nodes ? t.size[t.desc.root] : 0u;
+    t.layout_nodes = (uint32_t)t.huge.size() + (rest ? layout_slots(rest, true) - (rest > 1 ? 1u : 0u) : 0u);
+    return RTB_OK;
+}
+static void sah_emit(const RtbSceneDesc* desc, const SahTree& t, const std::vector<uint32_t>& quad_slot, int octant,
+                     float4* out) {
+    for (size_t h = 0; h < t.huge.size(); ++h) leaf_record(desc, (uint32_t)t.huge[h], quad_slot, &out[2 * h], &out[2 * h + 1]);
+    emit_layout(&t.desc, t.size, quad_slot, octant, true, out, true, (uint32_t)t.huge.size());
+}
+
 static void scene_free(RtbScene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
@@ -534,21 +588,13 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
             emit_layout(desc, size, quad_slot, oct, mode == 1, oct_nodes[mode].data() + (size_t)oct * oct_stride);
     }
     {  // mode 2: the library's own SAH partition of the objects the host's tree references
-        std::vector<RtbBvhNode> sah_nodes;
-        RtbSceneDesc sah = *desc;
-        sah.root = build_sah(desc, size, sah_nodes);
-        sah.nodes = sah_nodes.data();
-        sah.n_nodes = (uint32_t)sah_nodes.size();
-        std::vector<uint32_t> sah_size;
-        uint32_t sah_depth = 0;
-        rc = tree_sizes(&sah, sah_size, &sah_depth);
+        SahTree sah;
+        rc = sah_tree_build(desc, size, sah);
         if (rc != RTB_OK) return rc;
-        if (sah.n_nodes != n_tree) return fail(RTB_ERR_INVALID_ARGUMENT, "internal: SAH tree has %u nodes, expected %u", sah.n_nodes, n_tree);
-        n_tree_sah = layout_slots(n_tree, true) - (n_tree > 1 ? 1u : 0u);  // the root's own box is not emitted
+        n_tree_sah = sah.layout_nodes;
         const size_t sah_stride = 2 * ((size_t)n_tree_sah + 1);
         oct_nodes[2].assign(8 * sah_stride, sentinel);
-        for (int oct = 0; oct < 8; ++oct)
-            emit_layout(&sah, sah_size, quad_slot, oct, true, oct_nodes[2].data() + (size_t)oct * sah_stride, true);
+        for (int oct = 0; oct < 8; ++oct) sah_emit(desc, sah, quad_slot, oct, oct_nodes[2].data() + (size_t)oct * sah_stride);
     }
 
     RtbScene* sc = new (std::nothrow) RtbScene();
@@ -670,20 +716,17 @@ extern "C" int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, u
     for (uint32_t i = 0; i < desc->n_hittables; ++i)
         if (desc->hittables[i].type != RTB_HITTABLE_SPHERE) quad_slot[i] = append_complex(table, desc->hittables[i]);
     const uint32_t n_host = desc->n_nodes ? size[desc->root] : 0u;
-    const uint32_t n_tree = layout_slots(n_host, mode == RTB_TRAVERSAL_SAH) - (mode == RTB_TRAVERSAL_SAH && n_host > 1 ? 1u : 0u);
+    SahTree sah;
+    if (mode == RTB_TRAVERSAL_SAH) {
+        rc = sah_tree_build(desc, size, sah);
+        if (rc != RTB_OK) return rc;
+    }
+    const uint32_t n_tree = mode == RTB_TRAVERSAL_SAH ? sah.layout_nodes : n_host;
     *n_nodes_out = n_tree;
     if (!out_nodes) return RTB_OK;
     std::vector<float4> layout(2 * ((size_t)n_tree + 1), mkf4(0.0f, 0.0f, 0.0f, bits(RTB_META_END)));
     if (mode == RTB_TRAVERSAL_SAH) {
-        std::vector<RtbBvhNode> sah_nodes;
-        RtbSceneDesc sah = *desc;
-        sah.root = build_sah(desc, size, sah_nodes);
-        sah.nodes = sah_nodes.data();
-        sah.n_nodes = (uint32_t)sah_nodes.size();
-        std::vector<uint32_t> sah_size;
-        rc = tree_sizes(&sah, sah_size, &depth);
-        if (rc != RTB_OK) return rc;
-        emit_layout(&sah, sah_size, quad_slot, (int)octant, true, layout.data(), true);
+        sah_emit(desc, sah, quad_slot, (int)octant, layout.data());
     } else {
         emit_layout(desc, size, quad_slot, (int)octant, mode == RTB_TRAVERSAL_ORDERED, layout.data());
     }
