@@ -62,9 +62,11 @@ struct DevScene {
     // to (entry plane, exit plane) for the octant.  mode 0 = reference order, 1 = near-child-first,
     // 2 = the same objects re-partitioned by the library with a binned-SAH tree, near-child-first.
     // Each octant's array holds oct_n_nodes[mode] + 1 entries: the last one is the end sentinel (RTB_META_END).
-    // Modes 0 and 1 have the host tree's n_nodes entries; mode 2 additionally puts a BOX node (the object's
-    // own bounding box, skip = past the leaf) in front of every leaf, so a leaf is only tested when the ray
-    // enters its box, and the root's own box is not emitted (the walk starts with its two subtrees): 3n - 2 entries for n objects.
+    // Modes 0 and 1 have the host tree's n_nodes entries.  Mode 2 is laid out for speed, not for likeness: first the
+    // "huge" objects (box >= half of the scene's, e.g. the ground sphere) as plain leaves, then the SAH tree of the
+    // rest WITHOUT its root box (the walk starts with the root's two subtrees) and with a BOX node (the object's own
+    // padded box, skip = past the leaf) in front of every leaf, so a primitive is only tested when the ray enters
+    // its box: h + 3(n - h) - 2 entries for n objects of which h are huge.
     const float4* oct_nodes[3];
     uint32_t oct_n_nodes[3];
     // 4 per object: the leaf record {center1, kind|object}, {center_vec, radius} and the object's material
