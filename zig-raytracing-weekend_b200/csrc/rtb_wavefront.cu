@@ -173,13 +173,16 @@ __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
         if (slot < total) {
             uint32_t pixel;
             if (slot_pixel(P.R, slot % P.slots_per_sample, pixel)) {
+                // the path's Philox key (pixel, sample) rides in the two spare words of its (T, L) record, so that
+                // wf_shade does not have to recompute it from the slot (four 32-bit integer divisions per hit)
+                const uint32_t sample = P.batch_begin + slot / P.slots_per_sample;
                 P.TL[2u * (size_t)slot] = make_float4(1.f, 1.f, 1.f, 0.f);
-                P.TL[2u * (size_t)slot + 1u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                P.TL[2u * (size_t)slot + 1u] = make_float4(0.f, 0.f, __uint_as_float(pixel), __uint_as_float(sample));
                 if (P.R.cam.max_depth != 0u) {
                     RngKey key;
                     key.seed = P.R.seed;
                     key.pixel = pixel;
-                    key.sample = P.batch_begin + slot / P.slots_per_sample;
+                    key.sample = sample;
                     ray = get_ray(P.R.cam, key);
                     push = true;
                 }
@@ -287,12 +290,10 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
                 if (COUNT) ++n_hits;
                 const float4* __restrict__ pr = P.R.scene.prims + 4u * (size_t)e.z;
                 const float4 f0 = pr[0], f1 = pr[1], m0 = pr[2], m1 = pr[3];
-                uint32_t pixel;
-                slot_pixel(P.R, slot % P.slots_per_sample, pixel);
                 RngKey key;
                 key.seed = P.R.seed;
-                key.pixel = pixel;
-                key.sample = P.batch_begin + slot / P.slots_per_sample;
+                key.pixel = __float_as_uint(tl1.z);
+                key.sample = __float_as_uint(tl1.w);
                 const ShadeResult sr = shade_rec<QUADS>(P.R.scene, f0, f1, m0, m1, r, __uint_as_float(e.y), key, P.segment);
                 L = L + T * sr.emitted;
                 if (sr.scatters && P.segment < P.R.cam.max_depth) {
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
                 }
             }
             P.TL[2u * (size_t)slot] = make_float4(T.x, T.y, T.z, L.x);
-            P.TL[2u * (size_t)slot + 1u] = make_float4(L.y, L.z, 0.f, 0.f);
+            P.TL[2u * (size_t)slot + 1u] = make_float4(L.y, L.z, tl1.z, tl1.w);
         }
         push_ray(P, next, slot, push);
     }
