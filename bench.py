@@ -218,7 +218,14 @@ def run_ours(a):
     px = None
     if world_size > 1 and a.exchange != "nccl":
         # per-rank buffers owned by the library and mapped into every rank (CUDA IPC over NVLink/NVSwitch)
-        px = mg.PeerExchange(npx, rank, world_size, local_rank)
+        try:
+            px = mg.PeerExchange(npx, rank, world_size, local_rank)   # raises on EVERY rank if any rank cannot map
+        except RuntimeError as e:
+            if a.exchange == "p2p":
+                raise
+            print(f"[bench] peer-memory exchange unavailable, using NCCL: {e}", file=sys.stderr)
+            px = None
+    if px is not None:
         d_acc, d_rgba = px.accum, px.rgba
     else:
         d_acc = torch.zeros(npx, 4, device=dev, dtype=torch.float32)
@@ -237,7 +244,7 @@ def run_ours(a):
                                                      float(part.total_samples), local_rank, sptr), "rtb_resolve_device")
 
     exchange_probe = None
-    if world_size > 1 and a.exchange == "auto":   # measured, not assumed: both exchanges on this frame size, this box
+    if world_size > 1 and a.exchange == "auto" and px is not None:   # measured, not assumed: both exchanges on this frame size, this box
         part0 = mg.plan(a.partition, rank, world_size, a.spp, weak=(a.partition == "samples" and a.scaling == "weak"))
         times = {}
         for kind in ("p2p", "nccl"):

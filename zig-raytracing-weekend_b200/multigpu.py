@@ -111,6 +111,7 @@ class PeerExchange:
         lib = _ffi.rtb()
         self._own = []
         self._opened = []
+        self.accum = self.rgba = None
 
         def alloc(nbytes):
             p = C.c_void_p()
@@ -118,23 +119,43 @@ class PeerExchange:
             self._own.append(p.value)
             return p.value
 
-        self.accum_ptr = alloc(n_pixels * 16)
-        self.rgba_ptr = alloc(n_pixels * 4)
-        self.accum = torch.as_tensor(_DeviceArray(self.accum_ptr, (n_pixels, 4), "<f4"), device=f"cuda:{device}")
-        self.rgba = torch.as_tensor(_DeviceArray(self.rgba_ptr, (n_pixels, 4), "|u1"), device=f"cuda:{device}")
-        self.accum.zero_()
-        self.rgba.zero_()
+        def agree(ok, what, error):
+            """Every rank learns whether every rank succeeded, so that a local failure (out of memory, no IPC
+            permission) makes ALL ranks raise instead of leaving the others waiting in the next collective."""
+            if world == 1:
+                flags = [(ok, error)]
+            else:
+                flags = [None] * world
+                dist.all_gather_object(flags, (ok, error), group=group)
+            bad = [(r, e) for r, (k, e) in enumerate(flags) if not k]
+            if bad:
+                self._release()
+                raise RuntimeError(f"PeerExchange unavailable ({what}): " + "; ".join(f"rank {r}: {e}" for r, e in bad))
+
+        # 1. local buffers + their export handles
+        mine, error = [], None
+        try:
+            self.accum_ptr = alloc(n_pixels * 16)
+            self.rgba_ptr = alloc(n_pixels * 4)
+            self.accum = torch.as_tensor(_DeviceArray(self.accum_ptr, (n_pixels, 4), "<f4"), device=f"cuda:{device}")
+            self.rgba = torch.as_tensor(_DeviceArray(self.rgba_ptr, (n_pixels, 4), "|u1"), device=f"cuda:{device}")
+            self.accum.zero_()
+            self.rgba.zero_()
+            if world > 1:
+                for ptr in (self.accum_ptr, self.rgba_ptr):
+                    h = _ffi.RtbIpcHandle()
+                    _check(lib.rtb_ipc_export(device, ptr, C.byref(h)), "rtb_ipc_export")
+                    mine.append(bytes(h.bytes))
+        except Exception as e:  # noqa: BLE001 - reported to every rank below
+            error = str(e)
+        agree(error is None, "allocating / exporting the buffers", error)
         self.peer_accum = [None] * world
         self.peer_accum[rank] = self.accum_ptr
         self.root_accum, self.root_rgba = self.accum_ptr, self.rgba_ptr
         self._nccl = world > 1 and dist.get_backend(group) == "nccl"
         self._flag = torch.zeros(1, device=f"cuda:{device}") if self._nccl else None
+        # 2. map everybody else's buffers
         if world > 1:
-            mine = []
-            for ptr in (self.accum_ptr, self.rgba_ptr):
-                h = _ffi.RtbIpcHandle()
-                _check(lib.rtb_ipc_export(device, ptr, C.byref(h)), "rtb_ipc_export")
-                mine.append(bytes(h.bytes))
             everyone = [None] * world
             dist.all_gather_object(everyone, mine, group=group)
 
@@ -146,14 +167,29 @@ class PeerExchange:
                 self._opened.append(p.value)
                 return p.value
 
-            for r in range(world):
-                if r != rank:
-                    self.peer_accum[r] = open_(everyone[r][0])
-            if rank != root:
-                self.root_accum = self.peer_accum[root]
-                self.root_rgba = open_(everyone[root][1])
+            error = None
+            try:
+                for r in range(world):
+                    if r != rank:
+                        self.peer_accum[r] = open_(everyone[r][0])
+                if rank != root:
+                    self.root_accum = self.peer_accum[root]
+                    self.root_rgba = open_(everyone[root][1])
+            except Exception as e:  # noqa: BLE001
+                error = str(e)
+            agree(error is None, "mapping the peers' buffers", error)
             self.barrier()
         self._peers = (C.c_void_p * world)(*self.peer_accum)
+
+    def _release(self):
+        lib = self._ffi.rtb()
+        self.accum = self.rgba = None
+        for p in self._opened:
+            lib.rtb_ipc_close(self.device, p)
+        self._opened = []
+        for p in self._own:
+            lib.rtb_buffer_free(self.device, p)
+        self._own = []
 
     def slice(self):
         C = self._C
@@ -186,16 +222,9 @@ class PeerExchange:
         self.barrier()
 
     def close(self):
-        lib = self._ffi.rtb()
         if self.world > 1:
             try:
                 self.barrier()
-            except Exception:
+            except Exception:  # noqa: BLE001 - closing anyway
                 pass
-        self.accum = self.rgba = None
-        for p in self._opened:
-            lib.rtb_ipc_close(self.device, p)
-        self._opened = []
-        for p in self._own:
-            lib.rtb_buffer_free(self.device, p)
-        self._own = []
+        self._release()
