@@ -42,13 +42,16 @@ constexpr uint32_t kChunk = 256;  // hit records per CTA pass of wf_shade
 #endif
 constexpr uint32_t kExtendThreads = RTB_EXTEND_THREADS;
 #ifndef RTB_EXTEND_GRID_PER_SM
-#define RTB_EXTEND_GRID_PER_SM 4
+#define RTB_EXTEND_GRID_PER_SM 3
 #endif
 #ifndef RTB_SHADE_GRID_PER_SM
 #define RTB_SHADE_GRID_PER_SM 8
 #endif
 // wf_shade is bound by DRAM latency (gathers of 32-byte records): 5 CTAs per SM (<= 48 registers) instead of the 4
 // that 64 registers allow measured +7 % on the whole step.
+#ifndef RTB_EXTEND_CONTIGUOUS
+#define RTB_EXTEND_CONTIGUOUS 1
+#endif
 #ifndef RTB_SHADE_MINBLOCKS
 #define RTB_SHADE_MINBLOCKS 5
 #endif
@@ -212,7 +215,15 @@ __global__ void __launch_bounds__(kExtendThreads) wf_extend(const WfParams P) {
     uint32_t staged = kOctants;  // octant whose layout is in shared memory
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(rtb_smem_nodes) + P.zero;
     uint32_t n_box = 0, n_obj = 0, n_rays = 0;
+#if RTB_EXTEND_CONTIGUOUS
+    // A CTA walks a CONTIGUOUS range of chunks: the chunks are ordered by octant, so it stages one or two layouts per
+    // launch instead of all eight (a strided walk meets every octant).
+    const uint32_t per_cta = (total_chunks + gridDim.x - 1u) / gridDim.x;
+    const uint32_t c_end = (blockIdx.x + 1u) * per_cta < total_chunks ? (blockIdx.x + 1u) * per_cta : total_chunks;
+    for (uint32_t c = blockIdx.x * per_cta; c < c_end; ++c) {
+#else
     for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+#endif
         uint32_t oct = 0;
         while (c >= map.first_chunk[oct + 1u]) ++oct;
         const float4* __restrict__ nodes = layouts + (size_t)oct * oct_stride;
