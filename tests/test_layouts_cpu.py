@@ -149,3 +149,18 @@ def test_python_walk_of_every_layout_finds_the_oracle_hits(pkg, orc):
             total_obj[mode] += n_obj
     # SAH re-partition with box-tested leaves: far fewer slab tests and far fewer primitive tests
     assert total[1] <= total[0] and total[2] < 0.65 * total[0] and total_obj[2] < 0.35 * total_obj[0]
+
+
+def test_octant_from_sign_bits_equals_octant_from_reciprocal():
+    """push_ray bins rays by octant with ray_octant_of_direction (rtb_device.cuh): 0x80000000 <= bits(d) < 0xff800000.
+    It must equal Aabb.hit's own predicate `1/d < 0` (src/aabb.zig:97) for EVERY float, or a ray would be walked with
+    another octant's pre-swapped slabs."""
+    rng = np.random.default_rng(0)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, -np.nan, 1e-45, -1e-45, 3.4028235e38, -3.4028235e38,
+                        1.17549435e-38, -1.17549435e-38, 1.0, -1.0], np.float32)
+    bits = np.concatenate([special.view(np.uint32), rng.integers(0, 2 ** 32, 2_000_000, dtype=np.uint64).astype(np.uint32)])
+    d = bits.view(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = (np.float32(1.0) / d) < 0
+    got = (bits - np.uint32(0x80000000)) < np.uint32(0x7F800000)      # uint32 arithmetic wraps, like the device code
+    assert np.array_equal(got, want)

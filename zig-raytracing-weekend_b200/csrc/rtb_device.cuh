@@ -344,6 +344,14 @@ __device__ __forceinline__ uint32_t ray_octant(float inv_x, float inv_y, float i
     return (inv_x < 0.0f ? 1u : 0u) | (inv_y < 0.0f ? 2u : 0u) | (inv_z < 0.0f ? 4u : 0u);
 }
 
+// The same three predicates from the direction itself, without the divisions: 1/d < 0  <=>  d is negative, or -0
+// (1/-0 = -inf), but neither -inf (1/-inf = -0, not < 0) nor NaN  <=>  0x80000000 <= bits(d) < 0xff800000.
+__device__ __forceinline__ uint32_t ray_octant_of_direction(float3 d) {
+    const uint32_t x = __float_as_uint(d.x) - 0x80000000u, y = __float_as_uint(d.y) - 0x80000000u,
+                   z = __float_as_uint(d.z) - 0x80000000u;
+    return (x < 0x7f800000u ? 1u : 0u) | (y < 0x7f800000u ? 2u : 0u) | (z < 0x7f800000u ? 4u : 0u);
+}
+
 // Slab test against a node of a PER-OCTANT layout: f0.xyz already holds the plane the ray enters
 // through on each axis (min, or max where invD < 0) and f1.xyz the one it leaves through, so the
 // reference's swap is done once per (node, octant) on the host instead of per visit.  The values

@@ -135,7 +135,7 @@ __device__ __forceinline__ void warp_add(unsigned long long* dst, unsigned long 
 }
 
 __device__ __forceinline__ void push_ray(const WfParams& P, const DRay& ray, uint32_t slot, bool push) {
-    const uint32_t oct = push ? ray_octant(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z) : 0u;
+    const uint32_t oct = push ? ray_octant_of_direction(ray.d) : 0u;  // == ray_octant(1/d.x, 1/d.y, 1/d.z)
     const uint32_t j = queue_reserve(P.count_out, push, oct);
     if (push) {
         const size_t at = (size_t)oct * P.capacity + j;
