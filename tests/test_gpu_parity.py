@@ -518,3 +518,33 @@ print("ok", sa["n_launches"])
         assert st["n_paths"] == 2 * np.count_nonzero(acc[:, 3] == 2.0)
         total += st["n_paths"]
     assert total == 2 * cam.image_width * cam.image_height
+
+
+@pytest.mark.parametrize("forced", ["0", "1", "3", "12"])
+def test_wavefront_tail_switch_does_not_change_the_result(pkg, tmp_path, forced):
+    """wf_tail finishes the paths still alive after bounce k in one launch (the megakernel's loop, entered mid-path).
+    Where the switch happens is a performance decision — learned from the first batch, or forced here through
+    RTB_WF_TAIL_BOUNCE (0 = never, 1 = the whole path after the camera ray, ...) — and must not change a single bit."""
+    import subprocess
+    import sys
+    script = tmp_path / "tail.py"
+    script.write_text(f"""
+import importlib, sys
+import numpy as np
+sys.path.insert(0, {ROOT!r})
+pkg = importlib.import_module("zig-raytracing-weekend_b200")
+for world, camo in ((pkg.World.book1(), pkg.book1_camera(320, 5, 50)),
+                    (pkg.World.create(pkg.RTW_SCENE_CORNELL_SMOKE), pkg.cornell_camera(96, 4, 30))):
+    scene = pkg.Scene(world)
+    cam = camo.init()
+    for trav in (0, 2):
+        a, _, sa = scene.render(cam, pkg.render_options(seed=9, integrator=1, traversal=trav, flags=pkg.RTB_FLAG_COUNT_WORK))
+        b, _, sb = scene.render(cam, pkg.render_options(seed=9, integrator=0, traversal=trav, flags=pkg.RTB_FLAG_COUNT_WORK))
+        assert np.array_equal(a, b), "wavefront with tail switch differs from the megakernel"
+        for k in ("n_paths", "n_rays", "n_box_tests", "n_object_tests", "n_hits"):
+            assert sa[k] == sb[k], (k, sa[k], sb[k])
+print("ok")
+""")
+    env = dict(os.environ, RTB_WF_TAIL_BOUNCE=forced)
+    out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr

@@ -28,6 +28,7 @@
 #include <new>
 
 #include <cstdlib>
+#include <cstring>
 
 namespace rtb {
 
@@ -72,7 +73,12 @@ struct WfLane {
     uint32_t* counts = nullptr;  // [2][8] ray-queue sizes, then [2][8] hit-queue sizes
     cudaStream_t stream = nullptr;
     cudaEvent_t accumulated = nullptr;  // recorded after this lane's wf_accumulate
+    // survivors[b] = rays entering bounce b of the lane's latest batch, written by wf_extend into mapped pinned host
+    // memory (no copy, no synchronisation): how the host learns where the thin tail of a batch begins
+    uint32_t* survivors_host = nullptr;
+    uint32_t* survivors_dev = nullptr;
 };
+constexpr uint32_t kSurvivorSlots = 256;  // max_depth is a u8 in the reference (src/camera.zig:79)
 
 #ifndef RTB_WF_LANES
 #define RTB_WF_LANES 4
@@ -84,6 +90,10 @@ constexpr int kLanes = RTB_WF_LANES;
 
 struct WavefrontState {
     WfLane lanes[kLanes];
+    // bounce at which a batch of the last render became thin enough for wf_tail (0 = not known yet) and what it was
+    // learned for
+    uint32_t tail_bounce = 0, tail_depth = 0, tail_slots = 0;
+    const void* tail_scene = nullptr;
     cudaEvent_t begin = nullptr;
     int sm_count = 0;
     bool ready = false;
@@ -104,6 +114,7 @@ struct WfParams {
     uint32_t batch_samples;     // samples in flight per pixel in this batch
     uint32_t segment;           // 1-based segment index of the rays in `in`
     uint32_t zero;              // always 0; only there to make an address opaque to ptxas (see traverse_octant)
+    uint32_t* survivors;        // mapped host memory, [bounce] = rays entering that bounce (may be NULL)
 };
 
 __device__ __forceinline__ bool slot_pixel(const RenderParams& R, uint32_t r, uint32_t& pixel) {
@@ -208,6 +219,11 @@ __global__ void __launch_bounds__(kExtendThreads) wf_extend(const WfParams P) {
     if (blockIdx.x == 0 && threadIdx.x < kBins) {
         P.count_out[threadIdx.x] = 0u;
         P.hit_count_next[threadIdx.x] = 0u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.survivors && P.segment <= kSurvivorSlots) {
+        uint32_t total = 0;
+        for (uint32_t b = 0; b < kOctants; ++b) total += map.count[b];
+        P.survivors[P.segment - 1u] = total;
     }
     const uint32_t total_chunks = map.first_chunk[kBins];
     const size_t oct_stride = 2u * ((size_t)n_nodes + 1u);
@@ -321,6 +337,72 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
     if (COUNT) warp_add(&P.R.counters[3], n_hits);
 }
 
+// The thin tail of a batch.  After ~12 bounces of the Book-1 scene fewer than 1 % of the paths are alive, but the
+// per-bounce kernel pair still costs its launch + staging latency 38 more times (measured: bounces 12..50 = 10 % of the
+// step for < 1 % of the work).  wf_tail finishes every path that is still alive in ONE launch: a thread takes one ray of
+// the current queue and runs the rest of that path like the megakernel does — same traversal, same shading, same Philox
+// streams, so the result is bit-identical whichever bounce the switch happens at.
+template <bool COUNT, bool QUADS, bool FMA>
+__global__ void __launch_bounds__(256) wf_tail(const WfParams P) {
+    __shared__ ChunkMap map;
+    chunk_map_init(map, P.count_in, kOctants);
+    const uint32_t total_chunks = map.first_chunk[kBins];
+    const size_t oct_stride = 2u * ((size_t)P.R.scene.oct_n_nodes[P.R.ordered] + 1u);
+    const float4* __restrict__ layouts = P.R.scene.oct_nodes[P.R.ordered];
+    uint32_t n_rays = 0, n_box = 0, n_obj = 0, n_hits = 0;
+    for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+        uint32_t bin = 0;
+        while (c >= map.first_chunk[bin + 1u]) ++bin;
+        const uint32_t i = (c - map.first_chunk[bin]) * kChunk + threadIdx.x;
+        if (i >= map.count[bin]) continue;
+        const size_t at = (size_t)bin * P.capacity + i;
+        const float4 a = P.in.rays[2u * at];
+        const float4 b = P.in.rays[2u * at + 1u];
+        DRay ray;
+        ray.o = f3(a);
+        ray.time = a.w;
+        ray.d = f3(b);
+        const uint32_t slot = __float_as_uint(b.w);
+        const float4 tl0 = P.TL[2u * (size_t)slot];
+        const float4 tl1 = P.TL[2u * (size_t)slot + 1u];
+        float3 T = f3(tl0);
+        float3 L = f3(tl0.w, tl1.x, tl1.y);
+        RngKey key;
+        key.seed = P.R.seed;
+        key.pixel = __float_as_uint(tl1.z);
+        key.sample = __float_as_uint(tl1.w);
+        uint32_t segment = P.segment;
+        for (;;) {
+            if (COUNT) ++n_rays;
+            const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
+            const float4* __restrict__ nodes = layouts + (size_t)ray_octant(ix, iy, iz) * oct_stride;
+            const Nearest best = traverse_octant<COUNT, QUADS, false, FMA>(nodes, P.R.scene.quads, ray.o, ray.d, ray.time, ix,
+                                                                          iy, iz, 0.001f, __int_as_float(0x7f800000),
+                                                                          n_box, n_obj, 0u, key, segment);
+            if (best.node == 0xffffffffu) {
+                L = L + T * miss_color(P.R.cam, ray);
+                break;
+            }
+            if (COUNT) ++n_hits;
+            const float4* __restrict__ pr = P.R.scene.prims + 4u * (size_t)best.node;
+            const ShadeResult sr = shade_rec<QUADS>(P.R.scene, pr[0], pr[1], pr[2], pr[3], ray, best.t, key, segment);
+            L = L + T * sr.emitted;
+            if (!(sr.scatters && segment < P.R.cam.max_depth)) break;
+            T = T * sr.attenuation;
+            ray = sr.scattered;
+            ++segment;
+        }
+        P.TL[2u * (size_t)slot] = make_float4(T.x, T.y, T.z, L.x);
+        P.TL[2u * (size_t)slot + 1u] = make_float4(L.y, L.z, tl1.z, tl1.w);
+    }
+    if (COUNT) {
+        warp_add(&P.R.counters[0], n_rays);
+        warp_add(&P.R.counters[1], n_box);
+        warp_add(&P.R.counters[2], n_obj);
+        warp_add(&P.R.counters[3], n_hits);
+    }
+}
+
 __global__ void __launch_bounds__(256) wf_accumulate(const WfParams P) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P.slots_per_sample) return;
@@ -359,6 +441,7 @@ void wavefront_destroy(WavefrontState* st) {
     for (WfLane& ln : st->lanes) {
         lane_free(&ln);
         cudaFree(ln.counts);
+        if (ln.survivors_host) cudaFreeHost(ln.survivors_host);
         if (ln.stream) cudaStreamDestroy(ln.stream);
         if (ln.accumulated) cudaEventDestroy(ln.accumulated);
     }
@@ -376,6 +459,11 @@ static cudaError_t wf_init(WavefrontState* st) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.accumulated, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&ln.counts, 4 * kBins * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaHostAlloc(&ln.survivors_host, kSurvivorSlots * sizeof(uint32_t), cudaHostAllocMapped);
+        if (e == cudaSuccess) {
+            std::memset(ln.survivors_host, 0xff, kSurvivorSlots * sizeof(uint32_t));
+            e = cudaHostGetDevicePointer(&ln.survivors_dev, ln.survivors_host, 0);
+        }
     }
     st->ready = e == cudaSuccess;
     return e;
@@ -425,6 +513,23 @@ static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t
 // batch when run alone); on its own stream that tail overlaps the next batches' full-width bounces.
 // wf_accumulate calls are chained with events so every pixel still receives its samples in sample
 // order, i.e. the result stays bit-identical to the megakernel's and to a single-stream run.
+// First bounce at which at most 1/128 of the batch's paths (and at least a few thousand rays' worth of launches) are
+// still alive; max_depth + 1 if the batch never gets that thin.  survivors[b] = rays that entered bounce b.
+static uint32_t choose_tail_bounce(const uint32_t* survivors, uint32_t max_depth) {
+    const uint32_t first = survivors[0];
+    if (first == 0xffffffffu) return max_depth + 1u;
+    const uint32_t thresh = first / 128u > 4096u ? first / 128u : 4096u;
+    for (uint32_t b = 2; b < max_depth && b < kSurvivorSlots; ++b)
+        if (survivors[b] != 0xffffffffu && survivors[b] <= thresh) return b;
+    return max_depth + 1u;
+}
+// RTB_WF_TAIL_BOUNCE=k forces the switch bounce (k = 0: never switch, every bounce stays a kernel pair); used for A/B
+// measurements and by the test that the result does not depend on where the switch happens.  -1 = not forced.
+static int wf_forced_tail_bounce() {
+    static const int v = [] { const char* s = std::getenv("RTB_WF_TAIL_BOUNCE"); return s && s[0] ? std::atoi(s) : -1; }();
+    return v;
+}
+
 // Most path slots one pass may hold per sample (624 B each).  A frame with more owned pixels than this is rendered
 // in several passes over interleaved subsets of its tiles (every pixel belongs to exactly one pass, so the per-pixel
 // sample order is unchanged).  RTB_WF_MAX_SLOTS overrides it (tests force the multi-pass path on a small frame).
@@ -493,6 +598,11 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
 
     uint32_t launches = 0;
     int prev_lane = -1;
+    uint32_t tail_k = 0;
+    if (st->tail_scene == p.scene.nodes && st->tail_depth == p.cam.max_depth && st->tail_slots == slots_per_sample)
+        tail_k = st->tail_bounce;
+    if (wf_forced_tail_bounce() == 0) tail_k = p.cam.max_depth + 1u;  // never switches
+    else if (wf_forced_tail_bounce() > 0) tail_k = (uint32_t)wf_forced_tail_bounce();
     for (uint32_t batch = 0; batch < n_batches; ++batch) {
         const uint32_t s0 = batch * B;
         const uint32_t nb = (p.sample_count - s0 < B) ? p.sample_count - s0 : B;
@@ -519,11 +629,41 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         if (grid_e > (uint32_t)st->sm_count * RTB_EXTEND_GRID_PER_SM) grid_e = (uint32_t)st->sm_count * RTB_EXTEND_GRID_PER_SM;
         uint32_t grid_s = (cap + 255u) / 256u + kBins;
         if (grid_s > (uint32_t)st->sm_count * RTB_SHADE_GRID_PER_SM) grid_s = (uint32_t)st->sm_count * RTB_SHADE_GRID_PER_SM;
+        // Where does the thin tail begin?  Known from the last render of this scene, or learned now: batch 0 runs
+        // every bounce as a kernel pair and reports how many rays entered each; when its lane comes up for reuse the
+        // host waits for it (the other lanes keep the GPU busy meanwhile) and picks the switch bounce for the rest.
+        if (tail_k == 0u && batch == (uint32_t)lanes_used) {
+            e = cudaEventSynchronize(st->lanes[0].accumulated);
+            if (e != cudaSuccess) return e;
+            tail_k = choose_tail_bounce(st->lanes[0].survivors_host, p.cam.max_depth);
+            st->tail_bounce = tail_k;
+            st->tail_depth = p.cam.max_depth;
+            st->tail_scene = p.scene.nodes;
+            st->tail_slots = slots_per_sample;
+        }
+        P.survivors = (tail_k == 0u && batch == 0u) ? ln.survivors_dev : nullptr;
+        if (P.survivors) std::memset(ln.survivors_host, 0xff, kSurvivorSlots * sizeof(uint32_t));
         wf_raygen<<<grid, 256, 0, ln.stream>>>(P);
         ++launches;
         for (uint32_t bounce = 0; bounce < p.cam.max_depth; ++bounce) {
             P.in = ln.q[cur];
             P.count_in = ln.counts + cur * kBins;
+            if (tail_k != 0u && bounce >= tail_k) {  // everything still alive finishes in one launch
+                P.segment = bounce + 1u;
+                const uint32_t grid_t = (uint32_t)st->sm_count * 4u;
+#define RTB_TAIL(C, Q)                                                                         \
+    do {                                                                                       \
+        if (p.ordered == 2u) wf_tail<C, Q, true><<<grid_t, 256, 0, ln.stream>>>(P);            \
+        else                 wf_tail<C, Q, false><<<grid_t, 256, 0, ln.stream>>>(P);           \
+    } while (0)
+                if (count_work) { if (quads) RTB_TAIL(true, true); else RTB_TAIL(true, false); }
+                else            { if (quads) RTB_TAIL(false, true); else RTB_TAIL(false, false); }
+#undef RTB_TAIL
+                e = cudaGetLastError();
+                if (e != cudaSuccess) return e;
+                ++launches;
+                break;
+            }
             P.out = ln.q[cur ^ 1];
             P.count_out = ln.counts + (cur ^ 1) * kBins;
             P.hit_count = ln.counts + (2u + (bounce & 1u)) * kBins;
