@@ -439,7 +439,7 @@ def run_ours(a):
     achieved_tflops = flops_per_path * paths_per_launch_group / (kernel_ms * 1e-3) / 1e12
     achieved_gbs = (bytes_per_path * paths_per_launch_group + 20 * npx) / (kernel_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "fp32", "kernel": "render_megakernel" if integ_name == "megakernel" else "wf_raygen+wf_extend+wf_shade+wf_accumulate",
+        "bound": "fp32", "kernel": "render_megakernel" if integ_name == "megakernel" else "wf_raygen+wf_extend+wf_shade+wf_tail+wf_accumulate",
         "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
         "peak_source": "FFMA microbenchmark measured in this run (FMA = 2 flops); the kernels run unfused, ceiling = peak/2",
         # DRAM bytes of one step, from the ncu capture in profiles/r1g_dram_summary.csv (dram__bytes_read+write summed

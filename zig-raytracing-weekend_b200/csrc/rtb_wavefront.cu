@@ -20,9 +20,11 @@
 //   * HIT queues are binned by SHADING CLASS (miss / lambertian / metal / dielectric / other): ncu
 //     showed the shade kernel executing every material's code in every warp (890 warp-instructions per
 //     warp, 11-18 of 32 lanes active); with one class per 256-ray chunk a warp runs one material path.
-// Three persistent variants of the extend kernel (per-lane refill from the queue, with and without
-// leaf batching / while-while) were measured on B200 and all lost to the plain one-thread-per-ray
-// loop, so they are not kept.
+// Once a batch has become thin (a fraction of a percent of its paths alive, bounce ~14 of 50 on Book-1) the
+// remaining paths are finished by ONE launch of wf_tail instead of dozens of nearly empty kernel pairs.
+// Five dynamic-ray-fetch variants of the extend kernel (per-lane and thresholded refill, with and without
+// leaf batching / while-while, with a guard-free self-looping sentinel) were measured on B200 and all lost
+// to the plain one-thread-per-ray loop, so they are not kept.
 #include "rtb_wavefront.cuh"
 
 #include <new>
