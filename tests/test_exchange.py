@@ -60,7 +60,7 @@ def _expected(parts, spp, orc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8, 16])
 def test_exchange_resolve_kernel_matches_numpy_and_oracle(pkg, orc, world):
     import torch
     lib = pkg._ffi.rtb()
