@@ -423,27 +423,29 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
     best.node = 0xffffffffu;
     const float a = length_squared(d);
     const float nox = -(o.x * inv_x), noy = -(o.y * inv_y), noz = -(o.z * inv_z);  // FMA only
-    uint32_t i = 0;
+    // SMEM: `i` is the node's 32-bit shared-window ADDRESS and the skip links of the staged copy are addresses too
+    // (the staging loop rewrites them, see wf_extend), which saves the index -> address instruction of every visit.
+    uint32_t i = SMEM ? smem_base : 0u;
     for (;;) {
         float4 f0, f1;
         if (SMEM) {
-            const uint32_t addr = smem_base + i * 32u;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(f0.x), "=f"(f0.y), "=f"(f0.z), "=f"(f0.w)
-                         : "r"(addr));
+                         : "r"(i));
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];"
                          : "=f"(f1.x), "=f"(f1.y), "=f"(f1.z), "=f"(f1.w)
-                         : "r"(addr));
+                         : "r"(i));
         } else {
             f0 = nodes[2u * i];
             f1 = nodes[2u * i + 1u];
         }
+        constexpr uint32_t kStep = SMEM ? 32u : 1u;
         const uint32_t meta = __float_as_uint(f0.w);
-        if (meta < (1u << 30)) {  // KIND_INTERIOR: meta is the skip index
+        if (meta < (1u << 30)) {  // KIND_INTERIOR: meta is the skip link
             if (COUNT) ++n_box;
             const bool miss = FMA ? slab_miss_fma(f0, f1, inv_x, inv_y, inv_z, nox, noy, noz, t_min, best.t)
                                   : slab_miss_preswapped(f0, f1, o, inv_x, inv_y, inv_z, t_min, best.t);
-            i = miss ? meta : i + 1u;
+            i = miss ? meta : i + kStep;
         } else {
             if (meta == RTB_META_END) break;
             if (COUNT) ++n_obj;
@@ -467,7 +469,7 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
                     best.node = meta & RTB_META_INDEX_MASK;
                 }
             }
-            i = i + 1u;
+            i = i + kStep;
         }
     }
     return best;

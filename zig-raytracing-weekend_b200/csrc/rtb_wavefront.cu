@@ -247,7 +247,13 @@ __global__ void __launch_bounds__(kExtendThreads) wf_extend(const WfParams P) {
         const float4* __restrict__ nodes = layouts + (size_t)oct * oct_stride;
         if (SMEM_NODES && oct != staged) {
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < (uint32_t)oct_stride; i += blockDim.x) rtb_smem_nodes[i] = nodes[i];
+            // copy, turning the skip links (node indices) of interior nodes into shared-window addresses
+            for (uint32_t i = threadIdx.x; i < (uint32_t)oct_stride; i += blockDim.x) {
+                float4 v = nodes[i];
+                const uint32_t meta = __float_as_uint(v.w);
+                if ((i & 1u) == 0u && meta < (1u << 30)) v.w = __uint_as_float(smem_base + meta * 32u);
+                rtb_smem_nodes[i] = v;
+            }
             __syncthreads();
             staged = oct;
         }
