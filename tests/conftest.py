@@ -21,8 +21,10 @@ def pytest_configure(config):
 
 
 def _make(directory, target):
-    if not os.path.exists(os.path.join(directory, target)):
-        subprocess.run(["make", "-C", directory, "-j8"], check=True, stdout=subprocess.DEVNULL)
+    # Always: make is incremental, and a prebuilt .so that is older than an edited source must not pass the tests
+    # (the .so files are git-ignored and travel to the GPU box with the snapshot).
+    subprocess.run(["make", "-C", directory, "-j8"], check=True, stdout=subprocess.DEVNULL)
+    assert os.path.exists(os.path.join(directory, target))
 
 
 @pytest.fixture(scope="session")

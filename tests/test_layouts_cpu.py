@@ -164,3 +164,27 @@ def test_octant_from_sign_bits_equals_octant_from_reciprocal():
         want = (np.float32(1.0) / d) < 0
     got = (bits - np.uint32(0x80000000)) < np.uint32(0x7F800000)      # uint32 arithmetic wraps, like the device code
     assert np.array_equal(got, want)
+
+
+def test_sah_leaf_box_of_a_non_axis_aligned_quad_covers_all_four_corners(pkg):
+    """Quad.init's box is fromPoints(q, q+u+v).pad() (src/objects.zig:209) — the diagonal only.  The reference never
+    box-tests a leaf, the SAH layout does, so its leaf box must cover q+u and q+v too (a diamond quad
+    q=(0,0,0), u=(1,1,0), v=(1,-1,0) spans y in [-1,1] but its host box is y in +-5e-5)."""
+    w = pkg.World.new()
+    w.add_quad((0, 0, 0), (1, 1, 0), (1, -1, 0), pkg.material_spec())
+    w.add_sphere((0, 0, -5), 0.5, pkg.material_spec())
+    w.add_sphere((3, 0, -5), 0.5, pkg.material_spec())
+    w.build()
+    d = w.desc.contents                                   # constructTree sorts the object list in place (bvh.zig:64)
+    quad = [i for i in range(d.n_hittables) if d.hittables[i].type == pkg.RTB_HITTABLE_QUAD][0]
+    host = w.object_box(quad)
+    assert host[4] - host[1] < 1e-3                       # the reference's (short) box, kept as is on the host side
+    for octant in range(8):
+        L, n = _layout(pkg, w, 2, octant)
+        meta = L[:n, 3].view(np.uint32)
+        leaf = np.nonzero((meta >> 30 == 3) & ((meta & 0x3FFFFFFF) == quad))[0]
+        assert len(leaf) == 1 and meta[leaf[0] - 1] == leaf[0] + 1     # its box node sits right in front of it
+        box = L[leaf[0] - 1]
+        lo, hi = np.minimum(box[:3], box[4:7]), np.maximum(box[:3], box[4:7])
+        corners = np.array([(0, 0, 0), (1, 1, 0), (1, -1, 0), (2, 0, 0)], np.float32)
+        assert (lo <= corners.min(axis=0)).all() and (hi >= corners.max(axis=0)).all()

@@ -3,6 +3,11 @@
 
   ncu_summary.py launches <launches.csv> <out.csv>    per-kernel totals and share of the step (gpu__time_duration)
   ncu_summary.py full <report.ncu-rep> <out.csv>      the metrics DESIGN.md cites, one row per captured launch
+  ncu_summary.py dram <dram.csv> <out.csv> <n_paths> <key> [<note>]
+        per-kernel dram__bytes_read/write summed over EVERY launch of one render (ncu --metrics
+        dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:wf_ ...), divided by the render's
+        path count; also records the total under <key> in profiles/dram_per_path.json, which bench.py READS for
+        roofline.traffic (nothing is typed into bench.py).
 """
 import collections
 import csv
@@ -57,5 +62,41 @@ def full(rep, dst):
             print(" | ".join(f"{r[idx[k]]}" for k in keep[:11]))
 
 
+def dram(src, dst, n_paths, key, note=""):
+    import json
+    import os
+    n_paths = int(n_paths)
+    rd, wr, tm, cnt = collections.Counter(), collections.Counter(), collections.Counter(), collections.Counter()
+    for r in csv.reader(open(src)):
+        if len(r) < 15 or not r[0].isdigit():
+            continue
+        name, metric, val = r[4].split("(")[0], r[12], float(r[14])
+        if metric == "dram__bytes_read.sum":
+            rd[name] += val
+            cnt[name] += 1
+        elif metric == "dram__bytes_write.sum":
+            wr[name] += val
+        elif metric == "gpu__time_duration.sum":
+            tm[name] += val
+    total = 0.0
+    with open(dst, "w") as f:
+        w = csv.writer(f)
+        w.writerow([f"# {note}"])
+        w.writerow(["kernel", "launches", "dram_read_bytes", "dram_write_bytes", "time_us", "bytes_per_path"])
+        for k in rd:
+            bpp = (rd[k] + wr[k]) / n_paths
+            total += bpp
+            w.writerow([k, cnt[k], int(rd[k]), int(wr[k]), round(tm[k] / 1e3, 1), round(bpp, 1)])
+            print(f"{k:50s} n={cnt[k]:4d} {bpp:8.1f} B/path {tm[k] / 1e3:9.1f} us")
+        w.writerow(["total", sum(cnt.values()), int(sum(rd.values())), int(sum(wr.values())),
+                    round(sum(tm.values()) / 1e3, 1), round(total, 1)])
+    print(f"total {total:.1f} B/path")
+    reg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "dram_per_path.json")
+    table = json.load(open(reg)) if os.path.exists(reg) else {}
+    table[key] = {"bytes_per_path": round(total, 1), "source": os.path.relpath(dst, os.path.dirname(os.path.dirname(reg))),
+                  "per_kernel": {k: round((rd[k] + wr[k]) / n_paths, 1) for k in rd}, "note": note}
+    json.dump(table, open(reg, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "dram": dram}[sys.argv[1]](*sys.argv[2:])

@@ -260,11 +260,11 @@ class Scene:
         _check(_ffi.rtb().rtb_render_async(self._h, C.byref(cam), C.byref(options), accum.ctypes.data,
                                            rgba.ctypes.data if rgba is not None else None, C.byref(job)),
                "rtb_render_async")
-        return Job(job, (accum, rgba, cam, options))
+        return Job(job, (accum, rgba, cam, options, self))   # the job's worker uses the scene until it is waited for
 
     def close(self):
         if self._h:
-            _ffi.rtb().rtb_scene_destroy(self._h)
+            _ffi.rtb().rtb_scene_destroy(self._h)   # waits for renders in flight on this scene (takes its mutex)
             self._h = None
 
     def __del__(self):

@@ -360,6 +360,25 @@ static int32_t build_sah(const RtbSceneDesc* d, const std::vector<uint32_t>& rea
             it.c[a] = 0.5f * (nd.bmin[a] + nd.bmax[a]);
         }
         it.object = nd.leaf;
+        // Quad.init's box is fromPoints(q, q + u + v).pad() (src/objects.zig:209): the two far corners only, which does
+        // not cover a quad that is not axis-aligned (q + u and q + v may lie outside it).  The reference never box-tests
+        // a leaf (src/bvh.zig:123-125), so there the short box only loosens the parents; this tree DOES box-test its
+        // leaves, so the leaf box is widened to all four corners, padded like Aabb.pad (src/aabb.zig:36-43).
+        const RtbHittable& h = d->hittables[nd.leaf];
+        if (h.type == RTB_HITTABLE_QUAD) {
+            for (int a = 0; a < 3; ++a) {
+                const float c0 = h.a[a], c1 = h.a[a] + h.b[a], c2 = h.a[a] + h.c[a], c3 = h.a[a] + h.b[a] + h.c[a];
+                float lo = std::fmin(std::fmin(c0, c1), std::fmin(c2, c3));
+                float hi = std::fmax(std::fmax(c0, c1), std::fmax(c2, c3));
+                if (hi - lo < 0.0001f) {  // Interval.expand(delta) of a thin axis
+                    lo -= 0.00005f;
+                    hi += 0.00005f;
+                }
+                it.bmin[a] = std::fmin(it.bmin[a], lo);
+                it.bmax[a] = std::fmax(it.bmax[a], hi);
+                it.c[a] = 0.5f * (it.bmin[a] + it.bmax[a]);
+            }
+        }
         items.push_back(it);
     }
     // Pad every object box outwards by 2^-21 of the scene's extent on that axis.  The SAH layouts box-test the
@@ -736,6 +755,10 @@ extern "C" int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, u
 
 extern "C" int rtb_scene_destroy(RtbScene* scene) {
     if (!scene) return RTB_OK;
+    // A render in flight on this scene (rtb_render_async's worker, or another thread's rtb_render) holds the mutex:
+    // wait for it instead of freeing the queues under it.  Jobs must still be waited for / destroyed by the caller
+    // before the scene is destroyed if they have batches left to start (rtb.h).
+    { std::lock_guard<std::mutex> lock(scene->mutex); }
     scene_free(scene);
     return RTB_OK;
 }

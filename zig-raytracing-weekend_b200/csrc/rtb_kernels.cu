@@ -251,11 +251,24 @@ __global__ void __launch_bounds__(256) resolve_kernel(const float4* __restrict__
     }
 }
 
+// SM count of the current device (grids are sized in multiples of it), queried once per device.
+uint32_t current_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148u;
+    if (cached[dev] == 0) {
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148u;
+        cached[dev] = sms;
+    }
+    return (uint32_t)cached[dev];
+}
+
 cudaError_t launch_resolve(const float4* d_accum, uchar4* d_rgba, uint64_t n_pixels, float n_override,
                            cudaStream_t stream) {
     if (n_pixels == 0) return cudaSuccess;
     uint64_t blocks = (n_pixels + 255u) / 256u;
-    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    const uint64_t cap = (uint64_t)current_sm_count() * 16u;
+    if (blocks > cap) blocks = cap;
     resolve_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(d_accum, d_rgba, n_pixels, n_override);
     return cudaGetLastError();
 }
@@ -345,7 +358,8 @@ cudaError_t launch_exchange_resolve(const PeerAccums& peers, uint32_t world, flo
     static const int bps = [] { const char* s = std::getenv("RTB_XCHG_BLOCKS_PER_SM"); return s ? std::atoi(s) : 8; }();
     const int p = ppt == 4 ? 4 : (ppt == 2 ? 2 : 1);
     uint64_t blocks = (end - begin + 256u * p - 1u) / (256u * p);
-    if (blocks > 148u * (uint64_t)(bps > 0 ? bps : 8)) blocks = 148u * (uint64_t)(bps > 0 ? bps : 8);
+    const uint64_t cap = (uint64_t)current_sm_count() * (uint64_t)(bps > 0 ? bps : 8);
+    if (blocks > cap) blocks = cap;
     const uint32_t g = (uint32_t)blocks;
     if (p == 4) exchange_dispatch<4>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel, g, stream);
     else if (p == 2) exchange_dispatch<2>(peers, world, root_accum, root_rgba, begin, end, samples_per_pixel, g, stream);

@@ -52,6 +52,9 @@ cudaError_t launch_philox_selftest(const uint4* d_ctr, uint2 key, uint32_t n, ui
 // FFMA-chain microbenchmark (roofline denominator): out must hold grid*256 floats.
 cudaError_t launch_ffma_peak(float* d_out, uint32_t grid, uint32_t iters, cudaStream_t stream);
 
+// Number of SMs of the current device.
+uint32_t current_sm_count();
+
 // Largest dynamic shared memory the megakernel may use for the node array.
 size_t megakernel_max_smem_nodes_bytes();
 

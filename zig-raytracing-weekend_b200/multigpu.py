@@ -199,27 +199,37 @@ class PeerExchange:
                     "rtb_exchange_slice")
         return b.value, e.value
 
-    def barrier(self):
-        """Orders the CUDA work of all ranks: nothing queued after it starts before everything queued before it, on
-        every rank, has finished."""
+    def barrier(self, stream: int | None = None):
+        """Orders the CUDA work of all ranks: nothing queued after it on `stream` starts before everything queued
+        before it, on every rank, has finished.  `stream` = raw cudaStream_t of the stream the exchange kernel runs on
+        (None = torch's current stream); the NCCL all-reduce is issued ON that stream, so it orders the kernel."""
         if self.world == 1:
             return
         import torch
         import torch.distributed as dist
         if self._nccl:
-            dist.all_reduce(self._flag, group=self.group)
+            if stream is None or stream == torch.cuda.current_stream(self.device).cuda_stream:
+                dist.all_reduce(self._flag, group=self.group)
+            else:
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=self.device)):
+                    dist.all_reduce(self._flag, group=self.group)
         else:
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)
 
-    def exchange(self, samples_per_pixel: float, stream: int = 0):
-        """barrier -> rtb_exchange_resolve on every rank -> barrier.  Afterwards rank `root`'s `accum` holds the
-        combined sums (.w = samples_per_pixel) and its `rgba` the resolved frame."""
-        self.barrier()
+    def exchange(self, samples_per_pixel: float, stream: int | None = None):
+        """barrier -> rtb_exchange_resolve on every rank -> barrier, all on `stream` (raw cudaStream_t; None = torch's
+        current stream).  Afterwards rank `root`'s `accum` holds the combined sums (.w = samples_per_pixel) and its
+        `rgba` the resolved frame.  NOTE: root's `accum` then holds the COMBINED sums — zero every rank's `accum`
+        before rendering the next frame into it."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.barrier(stream)
         self._check(self._ffi.rtb().rtb_exchange_resolve(self._peers, self.world, self.rank, self.root, self.root_accum,
                                                          self.root_rgba, self.n_pixels, float(samples_per_pixel),
                                                          self.device, stream), "rtb_exchange_resolve")
-        self.barrier()
+        self.barrier(stream)
 
     def close(self):
         if self.world > 1:
