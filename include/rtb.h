@@ -218,7 +218,16 @@ enum {
      * (src/bvh.zig:48-67), and visits the near child first.  Slab test, primitive test and every hit
      * value are computed by the same code; only the set of visited nodes changes, so the same caveat
      * as ORDERED applies.  Not used by the hit-query parity harness unless asked for. */
-    RTB_TRAVERSAL_SAH = 2
+    RTB_TRAVERSAL_SAH = 2,
+    /* The SAH tree above, packed for the shared-memory walk of the wavefront integrator: a box node is ONE 16-byte
+     * slot — its six planes as binary16 pairs in the tree's own normalised frame, rounded outwards — and the slab test
+     * is three packed half-precision FMAs on (entry, exit) pairs whose per-ray constants carry an error margin, so the
+     * test is CONSERVATIVE: it may enter a box an exact test would cull, never the reverse.  Leaves keep the
+     * reference's f32 arithmetic, so t / p / normal of every hit are the same bits as in the other modes, and the set
+     * of leaves tested is a superset of RTB_TRAVERSAL_SAH's.  Half the shared-memory traffic and 12 instead of 18
+     * issue slots per node visit.  Used when the packed layout fits in shared memory
+     * (<= 96 KB per octant, ~3 000 objects); larger scenes render exactly as RTB_TRAVERSAL_SAH. */
+    RTB_TRAVERSAL_SAH16 = 3
 };
 
 enum {
@@ -361,6 +370,31 @@ int rtb_exchange_resolve(const float* const* peer_accum, uint32_t world, uint32_
                          float* root_accum_out, uint8_t* root_rgba_out, uint64_t n_pixels, float samples_per_pixel,
                          int device, void* cuda_stream);
 
+/* ---- multi-GPU behind ONE call (one process) -------------------------------------------------------------------
+ * The literal counterpart of startRender (src/main.zig:314-326), which starts all 8 strips of one frame with one call
+ * and lets them share one writer.buffer / texture_buffer (src/camera.zig:22-27): the caller creates a GROUP once — one
+ * replica of the scene per device — and renders with its host buffers; the library partitions the frame, runs one
+ * host thread per device, combines the per-device accumulators over peer memory (cudaDeviceEnablePeerAccess, i.e.
+ * NVLink / NVSwitch; the same fused kernel as rtb_exchange_resolve, every device its slice) before gamma and
+ * quantisation, and hands back ONE frame.  No launcher, rendezvous or IPC handles on the caller's side. */
+typedef struct RtbSceneGroup RtbSceneGroup;
+enum {
+    RTB_PARTITION_SAMPLES = 0, /* device r renders a contiguous range of the global sample indices (the union of the
+                                * paths is what one device would trace; sums differ by float association only) */
+    RTB_PARTITION_TILES = 1    /* device r renders the 32x8-pixel tiles t with t % n == r (disjoint pixels: the frame
+                                * is bit-identical to the single-device one) */
+};
+/* devices: CUDA ordinals, 1..16 entries; every pair must be peer-accessible (RTB_ERR_UNSUPPORTED otherwise).  An
+ * ordinal may be listed more than once (several replicas on one device: useful for tests on a single-GPU box). */
+int rtb_group_create(const RtbSceneDesc* desc, const int* devices, uint32_t n_devices, RtbSceneGroup** group_out);
+int rtb_group_destroy(RtbSceneGroup* group);
+int rtb_group_size(const RtbSceneGroup* group, uint32_t* n_devices_out);
+/* Like rtb_render: accum / rgba are HOST buffers of the whole frame; the samples are ADDED to accum and .w is set to
+ * sample_begin + sample_count.  options.pixel_* / tile_* must be 0 (the library partitions); integrator, traversal,
+ * seed, sample range and flags apply to every device.  stats: sums over the devices, device_ms = the slowest. */
+int rtb_group_render(RtbSceneGroup* group, const RtbCamera* camera, const RtbRenderOptions* options, uint32_t partition,
+                     float* accum, uint8_t* rgba, RtbRenderStats* stats);
+
 /* Progressive / cancellable render, preserving the GUI behaviour of the reference (progress
  * polling: countSamples src/main.zig:470-477; STOP: stopRender :328-336; per-sample refresh of
  * texture_buffer: src/camera.zig:57-65).  A worker thread renders `samples_per_launch` samples at
@@ -383,6 +417,13 @@ int rtb_philox_device_selftest(const uint32_t* counters4, const uint32_t* key2, 
  * to query the node count; otherwise it must hold 8 * (n_nodes + 1) floats. */
 int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, uint32_t octant, float* out_nodes,
                            uint32_t* n_nodes_out);
+
+/* Test hook (no device needed): the RTB_TRAVERSAL_SAH16 layout of one octant as raw 16-byte slots (4 words each; see
+ * DevScene::pk_nodes in csrc/rtb_device.cuh for the format), sentinel included, plus the normalised frame
+ * n = (x - center) / scale.  out_slots may be NULL to query *n_slots_out; otherwise it must hold 4 * n_slots words.
+ * Returns RTB_ERR_UNSUPPORTED when the scene is too large for the packed layout. */
+int rtb_debug_packed_layout(const RtbSceneDesc* desc, uint32_t octant, uint32_t* out_slots, uint32_t* n_slots_out,
+                            float center_out[3], float scale_out[3]);
 
 /* Measurement aid for the roofline: runs a dependent-chain FFMA microbenchmark (8 independent chains
  * per thread, full grid) on `device` and returns the best-of-5 rate in TFLOP/s counting one FMA as two

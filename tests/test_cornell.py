@@ -102,7 +102,7 @@ def test_box_and_cornell_trace_parity(pkg, orc):
         rays = _rays(pkg, rng, 30000, lo, hi)
         cpu = orc.trace_rays(world.desc, rays)
         assert (cpu["object"] >= 0).mean() > 0.01
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             gpu = scene.trace_rays(rays, traversal=mode)
             same = gpu["object"] == cpu["object"]
             assert np.array_equal(gpu["t"], cpu["t"]), mode            # the nearest t is the same in every mode
@@ -128,7 +128,7 @@ def test_cornell_render_parity(pkg, orc, integrator):
     world = pkg.World.create(pkg.RTW_SCENE_CORNELL_BOX)
     scene = pkg.Scene(world)
     cam = pkg.cornell_camera(width=96, spp=8, max_depth=200).init()
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         o = pkg.render_options(seed=3, integrator=integrator, traversal=mode, flags=pkg.RTB_FLAG_COUNT_WORK)
         g, _, gs = scene.render(cam, o)
         c, _, cs = orc.render(world.desc, cam, o, n_threads=8)
@@ -213,7 +213,7 @@ def test_constant_medium_trace_parity(pkg, orc):
         d = world.desc.contents
         is_medium = np.array([o >= 0 and d.hittables[o].type == pkg.RTB_HITTABLE_CONSTANT_MEDIUM for o in cpu["object"]])
         assert is_medium.sum() > 300
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             gpu = scene.trace_rays(rays, traversal=mode)
             same = gpu["object"] == cpu["object"]
             # log() differs by ulps between CUDA and glibc: a medium hit can flip only when the draw lands within an
@@ -233,7 +233,7 @@ def test_cornell_smoke_render_parity(pkg, orc, integrator):
     world = pkg.World.create(pkg.RTW_SCENE_CORNELL_SMOKE)
     scene = pkg.Scene(world)
     cam = pkg.cornell_camera(width=96, spp=8, max_depth=50).init()
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         o = pkg.render_options(seed=3, integrator=integrator, traversal=mode, flags=pkg.RTB_FLAG_COUNT_WORK)
         g, _, gs = scene.render(cam, o)
         c, _, cs = orc.render(world.desc, cam, o, n_threads=8)

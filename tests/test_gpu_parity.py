@@ -371,7 +371,7 @@ def test_full_size_properties_config2(pkg, book1):
     assert 2.0 < st["n_rays"] / st["n_paths"] < 6.0
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_ordered_traversal_agrees(pkg, orc, book1, mode):
     """RTB_TRAVERSAL_ORDERED (1: near-child-first per octant on the host's tree) and RTB_TRAVERSAL_SAH (2: the same
     objects re-partitioned by the library): same slab/sphere arithmetic, different set/order of visited nodes.  The
@@ -392,11 +392,11 @@ def test_ordered_traversal_agrees(pkg, orc, book1, mode):
     if bad.any():  # where they disagree the two candidate roots are within rounding of each other
         np.testing.assert_allclose(ref["t"][bad], ordr["t"][bad], rtol=1e-4)
     assert ordr["n_box_tests"].sum() <= ref["n_box_tests"].sum()
-    if mode == 2:  # the SAH partition must be much cheaper than the random-axis median-split tree
+    if mode >= 2:  # the SAH partition must be much cheaper than the random-axis median-split tree
         assert ordr["n_box_tests"].sum() < 0.6 * ref["n_box_tests"].sum()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("integrator", [0, 1])
 def test_ordered_render_matches_reference_order_render(pkg, orc, book1, integrator, mode):
     """Same Philox streams, ORDERED / SAH vs the ORACLE's reference-order render: identical paths except where a hit
@@ -410,6 +410,56 @@ def test_ordered_render_matches_reference_order_render(pkg, orc, book1, integrat
     assert np.count_nonzero(diff > 1e-4) <= 2e-3 * diff.shape[0]
     assert abs(sa["n_rays"] - sb["n_rays"]) <= 1e-3 * sa["n_rays"] and sa["n_paths"] == sb["n_paths"]
     assert sb["n_box_tests"] <= sa["n_box_tests"]
+
+
+def test_sah16_is_a_conservative_superset_of_sah(pkg, orc, book1, earthmap):
+    """RTB_TRAVERSAL_SAH16 walks the SAH tree with 16-byte packed box nodes and a half-precision slab test whose
+    constants carry an error margin: it may enter boxes the f32 test culls, never the reverse, and leaves keep the
+    reference's arithmetic.  So per ray: the same nearest hit as SAH (same bits in t), at least as many leaves tested,
+    a few per cent more box nodes visited; and the three kernels that walk the packed layout (ray queries, megakernel,
+    wavefront from shared memory) produce the same image bit for bit."""
+    world, scene = book1
+    cam = pkg.book1_camera(400, 10, 50).init()
+    rng = np.random.default_rng(23)
+    prim = _rays_from_camera(orc, cam, 5, 40000, rng)
+    sec = _secondary_rays(pkg, orc, world.desc, prim[:6000], orc.trace_rays(world.desc, prim[:6000]), 3)
+    stress = _random_rays(pkg, rng, 20000, -12, 12)
+    stress["direction"][:3000, 0] = 0.0          # axis-parallel: the axis is dropped from the packed test
+    stress["direction"][3000:6000, 1] *= 1e-7    # |1/d| beyond binary16
+    stress["origin"][6000:9000] *= 100.0         # far origins: the margin grows with |o|
+    rays = np.concatenate([prim, sec, stress])
+    s32 = scene.trace_rays(rays, traversal=pkg.RTB_TRAVERSAL_SAH)
+    s16 = scene.trace_rays(rays, traversal=pkg.RTB_TRAVERSAL_SAH16)
+    ref = orc.trace_rays(world.desc, rays)
+    assert (s16["n_object_tests"] >= s32["n_object_tests"]).all()
+    same = s16["object"] == s32["object"]
+    assert same.mean() >= 0.99995, int((~same).sum())
+    # where they differ SAH16 (the superset) must be the one that agrees with the reference, or all three are within
+    # rounding of each other
+    for k in np.nonzero(~same)[0]:
+        assert s16["object"][k] == ref["object"][k] or np.isclose(s16["t"][k], s32["t"][k], rtol=1e-4), int(k)
+    hit = same & (s32["object"] >= 0)
+    for f in ("t", "p", "normal", "front_face"):
+        assert np.array_equal(s16[f][hit], s32[f][hit]), f
+    assert (s16["object"] == ref["object"]).mean() >= 0.9999
+    n_ord = len(prim) + len(sec)
+    ratio = s16["n_box_tests"][:n_ord].sum() / s32["n_box_tests"][:n_ord].sum()
+    assert 1.0 <= ratio <= 1.08, ratio
+    cam2 = pkg.book1_camera(256, 6, 50).init()
+    a, _, sa = scene.render(cam2, pkg.render_options(seed=4, integrator=1, traversal=3, flags=pkg.RTB_FLAG_COUNT_WORK))
+    b, _, sb = scene.render(cam2, pkg.render_options(seed=4, integrator=0, traversal=3, flags=pkg.RTB_FLAG_COUNT_WORK))
+    assert np.array_equal(a, b)
+    for k in ("n_rays", "n_box_tests", "n_object_tests", "n_hits"):
+        assert sa[k] == sb[k], k
+    c, _, sc = scene.render(cam2, pkg.render_options(seed=4, integrator=1, traversal=2, flags=pkg.RTB_FLAG_COUNT_WORK))
+    assert np.count_nonzero(np.abs(a[:, :3] - c[:, :3]).max(axis=1) > 1e-4) <= 1e-3 * a.shape[0]
+    assert sc["n_box_tests"] <= sa["n_box_tests"] <= 1.08 * sc["n_box_tests"]
+    # a textured world (checker + image + noise): same check on the hit queries
+    tw = pkg.World.create(pkg.RTW_SCENE_TEXTURED, image=earthmap)
+    ts = pkg.Scene(tw)
+    trays = _random_rays(pkg, rng, 20000, -10, 10)
+    t32, t16 = ts.trace_rays(trays, traversal=2), ts.trace_rays(trays, traversal=3)
+    assert np.array_equal(t32["object"], t16["object"]) and np.array_equal(t32["t"], t16["t"])
 
 
 def test_wavefront_multi_batch_pipeline_bit_exact(pkg, book1):
@@ -537,7 +587,7 @@ for world, camo in ((pkg.World.book1(), pkg.book1_camera(320, 5, 50)),
                     (pkg.World.create(pkg.RTW_SCENE_CORNELL_SMOKE), pkg.cornell_camera(96, 4, 30))):
     scene = pkg.Scene(world)
     cam = camo.init()
-    for trav in (0, 2):
+    for trav in (0, 2, 3):
         a, _, sa = scene.render(cam, pkg.render_options(seed=9, integrator=1, traversal=trav, flags=pkg.RTB_FLAG_COUNT_WORK))
         b, _, sb = scene.render(cam, pkg.render_options(seed=9, integrator=0, traversal=trav, flags=pkg.RTB_FLAG_COUNT_WORK))
         assert np.array_equal(a, b), "wavefront with tail switch differs from the megakernel"

@@ -188,3 +188,163 @@ def test_sah_leaf_box_of_a_non_axis_aligned_quad_covers_all_four_corners(pkg):
         lo, hi = np.minimum(box[:3], box[4:7]), np.maximum(box[:3], box[4:7])
         corners = np.array([(0, 0, 0), (1, 1, 0), (1, -1, 0), (2, 0, 0)], np.float32)
         assert (lo <= corners.min(axis=0)).all() and (hi >= corners.max(axis=0)).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# RTB_TRAVERSAL_SAH16: 16-byte packed box nodes (binary16 planes) + conservative half2 slab test
+# ------------------------------------------------------------------------------------------------
+def _packed(pkg, world, octant):
+    n = C.c_uint32(0)
+    center, scale = (C.c_float * 3)(), (C.c_float * 3)()
+    lib = pkg._ffi.rtb()
+    assert lib.rtb_debug_packed_layout(world.desc, octant, None, C.byref(n), C.byref(center), C.byref(scale)) == 0
+    out = np.zeros((n.value, 4), np.uint32)
+    assert lib.rtb_debug_packed_layout(world.desc, octant, out.ctypes.data, C.byref(n), C.byref(center), C.byref(scale)) == 0
+    return out, np.array(list(center), np.float32), np.array(list(scale), np.float32)
+
+
+def _halves(words):
+    """uint32 -> (lo half, hi half) as float64"""
+    w = np.asarray(words, np.uint32)
+    lo = (w & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)
+    hi = (w >> 16).astype(np.uint16).view(np.float16).astype(np.float64)
+    return lo, hi
+
+
+@pytest.mark.parametrize("scene", ["book1", "quads", "cornell"])
+def test_packed_layout_contains_the_f32_layout(pkg, scene):
+    world = {"book1": lambda: pkg.World.book1(), "quads": lambda: pkg.World.create(pkg.RTW_SCENE_QUADS),
+             "cornell": lambda: pkg.World.create(pkg.RTW_SCENE_CORNELL_BOX)}[scene]()
+    for octant in range(8):
+        L, n = _layout(pkg, world, 2, octant)
+        S, center, scale = _packed(pkg, world, octant)
+        meta = L[:, 3].view(np.uint32)
+        # slot index of every entry of the f32 layout: box 1 slot, leaf 2, sentinel 1
+        size = np.where((meta < (1 << 30)) | (meta == END), 1, 2)
+        slot = np.concatenate([[0], np.cumsum(size)])[:-1]
+        assert len(S) == size.sum() and S[slot[n], 3] == END
+        for k in range(n):
+            s = S[slot[k]]
+            if meta[k] < (1 << 30):
+                assert s[3] == slot[meta[k]]                                   # skip link in slot units
+                e, x = _halves(s[:3])
+                e, x = e * scale + center, x * scale + center                   # back to world space (float64)
+                lo, hi = np.minimum(e, x), np.maximum(e, x)
+                blo, bhi = np.minimum(L[k, :3], L[k, 4:7]), np.maximum(L[k, :3], L[k, 4:7])
+                assert (lo <= blo).all() and (hi >= bhi).all()                   # contains the f32 box ...
+                assert (blo - lo <= scale * 2.0 ** -9).all() and (hi - bhi <= scale * 2.0 ** -9).all()   # ... tightly
+                for a in range(3):                                               # and keeps the pre-swapped order
+                    assert (x[a] <= e[a]) if (octant >> a) & 1 else (e[a] <= x[a])
+            else:
+                assert s[3] == meta[k] and (s[:3] == L[k, :3].view(np.uint32)).all()
+                assert S[slot[k] + 1, 3] & 0x80000000                            # a leaf's second slot is never a link
+                if meta[k] >> 30 != 3:
+                    assert np.float32(-abs(L[k, 7])).view(np.uint32) == S[slot[k] + 1, 3]
+                    assert (S[slot[k] + 1, :3] == L[k, 4:7].view(np.uint32)).all()
+
+
+def _walk_packed(S, center, scale, ray):
+    """traverse_packed (rtb_device.cuh) in Python: binary16 constants, one rounding per packed FMA."""
+    f = np.float32
+    h = lambda v: np.float64(np.float16(v))                      # round to binary16 (nearest even), back to float64
+    o, d, time = ray["origin"].astype(f), ray["direction"].astype(f), f(ray["time"])
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        I, N = np.zeros((3, 2)), np.zeros((3, 2))
+        terms = []
+        for a in range(3):
+            on = (o[a] - center[a]) * (f(1) / scale[a])
+            inv = scale[a] * (f(1) / d[a])
+            nod = -(on * inv)
+            terms.append((inv, nod, abs(inv) + abs(nod)))
+        m = max([t[2] for t in terms if t[2] < 3e38] + [f(0)])
+        e = (int(np.float32(m).view(np.uint32)) >> 23) - 127
+        sigma = f(2.0) ** -(min(e - 12, 120) if e > 12 else 0)          # t' = sigma * t fits binary16
+        for a, (inv, nod, mag) in enumerate(terms):
+            if not (mag < 3e38):
+                I[a], N[a] = (0, 0), (-np.inf, -np.inf)
+                continue
+            k = f(1.01) / f(2048)
+            E = mag * (f(1.01) / f(2048)) + f(1e-7)
+            I[a] = h(sigma * (inv * (f(1) - k))), h(sigma * -(inv * (f(1) + k)))
+            N[a] = h(sigma * (nod * (f(1) - k) - E)), h(sigma * (-(nod * (f(1) + k)) - E))
+        tmin = f(0.001)
+        rd = lambda v: np.float64(np.nextafter(np.float16(v), np.float16(-np.inf))) if np.float64(np.float16(v)) > v else np.float64(np.float16(v))
+        ru = lambda v: np.float64(np.nextafter(np.float16(v), np.float16(np.inf))) if np.float64(np.float16(v)) < v else np.float64(np.float16(v))
+        K = [rd(sigma * tmin), -np.inf]
+        best_t, best_obj = f(np.inf), -1
+        aa = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+        i, n_box, n_obj = 0, 0, 0
+        while True:
+            s = S[i]
+            m = int(s[3])
+            if m < (1 << 30):
+                n_box += 1
+                e, x = _halves(s[:3])
+                r = [K[0], K[1]]
+                for a in range(3):
+                    te, tx = h(e[a] * I[a][0] + N[a][0]), h(x[a] * I[a][1] + N[a][1])
+                    r[0] = np.fmax(r[0], te)
+                    r[1] = np.fmax(r[1], tx)
+                i = m if r[1] >= -r[0] else i + 1
+                continue
+            if m == END:
+                break
+            kind, obj = m >> 30, m & 0x3FFFFFFF
+            n_obj += 1
+            assert kind != 3
+            c1 = s[:3].view(f)
+            s1 = S[i + 1]
+            cv, radius = s1[:3].view(f), s1[3:4].view(f)[0]
+            c = c1 + (time * cv if kind == 2 else f(0))
+            oc = o - c
+            hb = oc[0] * d[0] + oc[1] * d[1] + oc[2] * d[2]
+            cc = (oc[0] * oc[0] + oc[1] * oc[1] + oc[2] * oc[2]) - radius * radius
+            disc = hb * hb - aa * cc
+            if disc >= 0:
+                sq = np.sqrt(disc)
+                root = (-hb - sq) / aa
+                if not (tmin < root < best_t):
+                    root = (-hb + sq) / aa
+                if tmin < root < best_t:
+                    best_t, best_obj = root, obj
+                    K[1] = -ru(sigma * root)
+            i += 2
+    return best_obj, best_t, n_box, n_obj
+
+
+def test_python_walk_of_the_packed_layout_finds_the_oracle_hits(pkg, orc):
+    world = pkg.World.book1()
+    cam = pkg.book1_camera(400, 10, 50).init()
+    rng = np.random.default_rng(5)
+    rays = orc.get_rays(cam, 9, rng.integers(0, 400 * 225, 150), 0)
+    extra = np.zeros(250, dtype=rays.dtype)
+    extra["origin"] = rng.uniform(-9, 9, (250, 3)).astype(np.float32)
+    extra["origin"][:, 1] = np.abs(extra["origin"][:, 1]) * 0.1 + 0.01
+    extra["direction"] = rng.normal(size=(250, 3)).astype(np.float32)
+    extra["direction"][:40, rng.integers(0, 3)] = 0.0                 # axis-parallel rays: that axis is dropped
+    extra["direction"][40:60, 1] *= 1e-6                              # nearly parallel: |1/d| overflows binary16
+    extra["origin"][60:80] *= 40.0                                    # far origins: the margin E grows with |o|
+    extra["time"] = rng.random(250).astype(np.float32)
+    extra["t_min"], extra["t_max"] = 0.001, np.inf
+    rays = np.concatenate([rays, extra])
+    cpu = orc.trace_rays(world.desc, rays)
+    layouts = {o: _packed(pkg, world, o) for o in range(8)}
+    f32_layouts = {o: _layout(pkg, world, 2, o) for o in range(8)}
+    tot16 = tot32 = 0
+    for k, ray in enumerate(rays):
+        bits = ray["direction"].view(np.uint32)
+        octant = sum((1 << a) for a in range(3) if np.uint32(bits[a] - np.uint32(0x80000000)) < 0x7F800000)
+        S, center, scale = layouts[octant]
+        obj, t, n_box, n_obj = _walk_packed(S, center, scale, ray)
+        assert obj == cpu["object"][k], k
+        if obj >= 0:
+            assert np.float32(t) == cpu["t"][k]
+        L, n = f32_layouts[octant]
+        _, _, n_box32, n_obj32 = _walk(L, n, None, ray)
+        assert n_obj >= n_obj32                                        # a superset of the leaves is tested
+        if k < 150 or k >= 150 + 80:                                   # ordinary rays (not the stress cases above)
+            tot16 += n_box
+            tot32 += n_box32
+        if 150 + 60 <= k < 150 + 80:                                   # far origins: scaled to fit binary16, not dropped
+            assert n_box <= n_box32 + 8, (k, n_box, n_box32)
+    assert tot32 <= tot16 <= 1.08 * tot32                              # ... at a small price in extra visits

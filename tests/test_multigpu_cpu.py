@@ -43,6 +43,30 @@ def test_plan_weak_and_tiles():
         mg.plan("rows", 0, 2, 8)
 
 
+def test_plan_rate_proportional_split():
+    """bench.py's N > 1 sample split follows the rate every rank showed in warm-up (a slower GPU gets fewer samples):
+    every sample exactly once, shares proportional to the weights, at least one sample per rank, identical on all
+    ranks (each rank computes the whole table from the all-gathered weights)."""
+    mg = _mg()
+    for world, weights in ((2, [1.0, 1.0]), (4, [1.0, 0.94, 1.0, 1.02]), (8, [1 / 124.1] + [1 / 131.8] * 7),
+                           (3, [1e-3, 1.0, 1.0])):
+        for spp, weak in ((500, True), (64, False), (1024, False), (8, False)):
+            parts = [mg.plan("samples", r, world, spp, sample_base=3, weak=weak, weights=weights) for r in range(world)]
+            total = spp * world if weak else spp
+            assert sum(p.sample_count for p in parts) == total and all(p.total_samples == total for p in parts)
+            covered = [s for p in parts for s in range(p.sample_begin, p.sample_begin + p.sample_count)]
+            assert covered == list(range(3, 3 + total))                 # contiguous, in rank order, no gap, no overlap
+            assert min(p.sample_count for p in parts) >= 1
+            if total >= 50 * world:
+                for p, w in zip(parts, weights):
+                    assert abs(p.sample_count - total * w / sum(weights)) <= 1.0 + 1e-9 or w == 1e-3
+    assert mg.split_samples(10, 4) == [3, 3, 2, 2]
+    with pytest.raises(ValueError):
+        mg.split_samples(3, 4)
+    with pytest.raises(ValueError):
+        mg.split_samples(30, 3, [1.0, 0.0, 1.0])
+
+
 def _tile_mask(width, height, rank, world):
     """Pixels of the 32x8 tiles with tile_index % world == rank (include/rtb.h: RtbRenderOptions.tile_rank)."""
     ys, xs = np.mgrid[0:height, 0:width]

@@ -106,7 +106,7 @@ def test_quad_scenes_trace_parity(pkg, orc, kind):
     rays = _rays(pkg, rng, 30000, -6, 8)
     cpu = orc.trace_rays(world.desc, rays)
     assert (cpu["object"] >= 0).mean() > 0.05
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         gpu = scene.trace_rays(rays, traversal=mode)
         assert np.array_equal(gpu["object"], cpu["object"]) and np.array_equal(gpu["front_face"], cpu["front_face"])
         hit = cpu["object"] >= 0
@@ -138,7 +138,7 @@ def test_coincident_quads_tie_follows_visiting_order(pkg, orc):
     assert np.array_equal(gpu["object"], cpu["object"]) and np.array_equal(gpu["t"], cpu["t"])
     on_pair = np.isin(cpu["object"], list(pair))
     assert on_pair.sum() > 200 and len(set(cpu["object"][on_pair].tolist())) == 1   # the reference always picks one
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         g = scene.trace_rays(rays, traversal=mode)
         assert np.array_equal(g["t"], cpu["t"])
         diff = g["object"] != cpu["object"]
@@ -166,7 +166,7 @@ def test_quad_scenes_render_parity(pkg, orc, kind, integrator):
     scene = pkg.Scene(world)
     cam = camo.init()
     spp = cam.samples_per_pixel
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         o = pkg.render_options(seed=77, integrator=integrator, traversal=mode, flags=pkg.RTB_FLAG_COUNT_WORK)
         g, g_rgba, gs = scene.render(cam, o)
         c, c_rgba, cs = orc.render(world.desc, cam, o, n_threads=8)

@@ -274,6 +274,41 @@ class Scene:
             pass
 
 
+class SceneGroup:
+    """rtb_group_*: one replica of the world per device, multi-GPU render behind one call (include/rtb.h)."""
+
+    def __init__(self, world: World, devices):
+        self.world = world
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        _check(_ffi.rtb().rtb_group_create(world.desc, arr, len(self.devices), C.byref(h)), "rtb_group_create")
+        self._h = h
+
+    def render(self, cam, options=None, partition=_ffi.RTB_PARTITION_SAMPLES, accum=None, want_rgba=True):
+        options = options if options is not None else render_options()
+        n = cam.image_width * cam.image_height
+        if accum is None:
+            accum, _ = new_writer(cam)
+        assert accum.dtype == np.float32 and accum.size == 4 * n and accum.flags.c_contiguous
+        rgba = np.zeros((n, 4), dtype=np.uint8) if want_rgba else None
+        st = _ffi.RtbRenderStats()
+        _check(_ffi.rtb().rtb_group_render(self._h, C.byref(cam), C.byref(options), partition, accum.ctypes.data,
+                                           rgba.ctypes.data if want_rgba else None, C.byref(st)), "rtb_group_render")
+        return accum, rgba, stats_dict(st)
+
+    def close(self):
+        if self._h:
+            _ffi.rtb().rtb_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Job:
     def __init__(self, handle, keep):
         self._h, self._keep = handle, keep

@@ -30,7 +30,7 @@ RTB_MAT_LAMBERTIAN, RTB_MAT_METAL, RTB_MAT_DIELECTRIC, RTB_MAT_DIFFUSE_LIGHT, RT
 RTB_TEX_SOLID, RTB_TEX_CHECKER, RTB_TEX_IMAGE, RTB_TEX_NOISE = range(4)
 RTB_BACKGROUND_SOLID, RTB_BACKGROUND_SKY = 0, 1
 RTB_INTEGRATOR_MEGAKERNEL, RTB_INTEGRATOR_WAVEFRONT = 0, 1
-RTB_TRAVERSAL_REFERENCE, RTB_TRAVERSAL_ORDERED, RTB_TRAVERSAL_SAH = 0, 1, 2
+RTB_TRAVERSAL_REFERENCE, RTB_TRAVERSAL_ORDERED, RTB_TRAVERSAL_SAH, RTB_TRAVERSAL_SAH16 = 0, 1, 2, 3
 RTB_FLAG_COUNT_WORK = 1
 
 RTW_SCENE_BOOK1, RTW_SCENE_EARTH, RTW_SCENE_TWO_SPHERES, RTW_SCENE_TWO_PERLIN, RTW_SCENE_TEXTURED, \
@@ -135,9 +135,11 @@ RTB_SYMBOLS = [
     "rtb_abi_version", "rtb_last_error", "rtb_device_count", "rtb_scene_create", "rtb_scene_destroy",
     "rtb_trace_rays", "rtb_render", "rtb_render_device", "rtb_resolve_device", "rtb_resolve", "rtb_render_async",
     "rtb_job_progress", "rtb_job_cancel", "rtb_job_wait", "rtb_job_destroy", "rtb_philox_device_selftest",
-    "rtb_measure_fp32_peak", "rtb_debug_build_layout", "rtb_buffer_alloc", "rtb_buffer_free", "rtb_ipc_export",
+    "rtb_measure_fp32_peak", "rtb_debug_build_layout", "rtb_debug_packed_layout", "rtb_buffer_alloc", "rtb_buffer_free", "rtb_ipc_export",
     "rtb_ipc_open", "rtb_ipc_close", "rtb_exchange_slice", "rtb_exchange_resolve",
+    "rtb_group_create", "rtb_group_destroy", "rtb_group_size", "rtb_group_render",
 ]
+RTB_PARTITION_SAMPLES, RTB_PARTITION_TILES = 0, 1
 RTW_SYMBOLS = [
     "rtw_world_create", "rtw_world_new", "rtw_world_add_image", "rtw_world_add_sphere", "rtw_world_add_quad",
     "rtw_world_add_box", "rtw_world_add_medium",
@@ -185,6 +187,8 @@ def rtb() -> C.CDLL:
     lib.rtb_philox_device_selftest.argtypes = [vp, vp, u32, vp, C.c_int]
     lib.rtb_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.rtb_debug_build_layout.argtypes = [C.POINTER(RtbSceneDesc), u32, u32, vp, C.POINTER(u32)]
+    lib.rtb_debug_packed_layout.argtypes = [C.POINTER(RtbSceneDesc), u32, vp, C.POINTER(u32), C.POINTER(f32 * 3),
+                                            C.POINTER(f32 * 3)]
     lib.rtb_buffer_alloc.argtypes = [C.c_int, u64, C.POINTER(vp)]
     lib.rtb_buffer_free.argtypes = [C.c_int, vp]
     lib.rtb_ipc_export.argtypes = [C.c_int, vp, C.POINTER(RtbIpcHandle)]
@@ -192,6 +196,11 @@ def rtb() -> C.CDLL:
     lib.rtb_ipc_close.argtypes = [C.c_int, vp]
     lib.rtb_exchange_slice.argtypes = [u64, u32, u32, u32, C.POINTER(u64), C.POINTER(u64)]
     lib.rtb_exchange_resolve.argtypes = [C.POINTER(vp), u32, u32, u32, vp, vp, u64, f32, C.c_int, vp]
+    lib.rtb_group_create.argtypes = [C.POINTER(RtbSceneDesc), C.POINTER(C.c_int), u32, C.POINTER(vp)]
+    lib.rtb_group_destroy.argtypes = [vp]
+    lib.rtb_group_size.argtypes = [vp, C.POINTER(u32)]
+    lib.rtb_group_render.argtypes = [vp, C.POINTER(RtbCamera), C.POINTER(RtbRenderOptions), u32, vp, vp,
+                                     C.POINTER(RtbRenderStats)]
     for s in RTB_SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("rtb_abi_version", "rtb_last_error"):

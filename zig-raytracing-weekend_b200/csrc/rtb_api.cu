@@ -17,6 +17,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "rtb_kernels.cuh"
 #include "rtb_wavefront.cuh"
 
@@ -72,6 +74,12 @@ struct RtbJob {
     std::string error;
     RtbRenderStats stats{};
 };
+
+// Library-internal (rtb_multi.cu): sets the calling thread's error message, returns `code`.
+extern "C" int rtb_set_last_error(int code, const char* message) {
+    g_last_error = message ? message : "";
+    return code;
+}
 
 extern "C" uint32_t rtb_abi_version(void) { return RTB_ABI_VERSION; }
 extern "C" const char* rtb_last_error(void) { return g_last_error.c_str(); }
@@ -563,6 +571,92 @@ static void sah_emit(const RtbSceneDesc* desc, const SahTree& t, const std::vect
     emit_layout(&t.desc, t.size, quad_slot, octant, true, out, true, (uint32_t)t.huge.size());
 }
 
+// RTB_TRAVERSAL_SAH16: the 8 SAH layouts (oct8 = [octant][2 * (n_entries + 1)] float4, as built by sah_emit) packed into
+// 16-byte slots — see DevScene::pk_nodes.  Box planes go to the normalised frame n = (x - center) / scale of the box
+// nodes' own bounds and are rounded OUTWARDS to binary16 (entry planes away from the box along the ray's direction of
+// travel, exit planes likewise), so a packed box always contains the f32 box it was made from.
+struct PackedLayout {
+    std::vector<uint4> slots;  // [octant][n_slots]
+    uint32_t n_slots = 0;      // per octant, sentinel included
+    float center[3] = {0, 0, 0}, scale[3] = {1, 1, 1};
+};
+static inline uint32_t fbits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+static inline uint32_t half_bits(__half h) {
+    uint16_t u;
+    std::memcpy(&u, &h, 2);
+    return u;
+}
+static void pack_layout(const std::vector<float4>& oct8, uint32_t n_entries, PackedLayout& out) {
+    const size_t stride = 2 * ((size_t)n_entries + 1);
+    // frame: bounds of the box nodes (octant 0 holds the same set of boxes as every other octant)
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t k = 0; k < n_entries; ++k) {
+        const float4 f0 = oct8[2 * (size_t)k], f1 = oct8[2 * (size_t)k + 1];
+        if (fbits(f0.w) >= (1u << 30)) continue;
+        const float lo[3] = {f0.x, f0.y, f0.z}, hi[3] = {f1.x, f1.y, f1.z};
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = std::fmin(mn[a], std::fmin(lo[a], hi[a]));
+            mx[a] = std::fmax(mx[a], std::fmax(lo[a], hi[a]));
+        }
+    }
+    for (int a = 0; a < 3; ++a) {
+        if (!(mn[a] <= mx[a])) mn[a] = mx[a] = 0.0f;  // no box nodes at all
+        out.center[a] = 0.5f * (mn[a] + mx[a]);
+        const float half = std::fmax(mx[a] - out.center[a], out.center[a] - mn[a]);
+        out.scale[a] = half > 0.0f ? half * 1.001f : 1.0f;
+    }
+    // slot index of every entry (box 1, leaf 2, sentinel 1); identical for all octants (same tree shape per octant?
+    // no — child order differs per octant, so the prefix is computed per octant)
+    out.n_slots = 0;
+    std::vector<uint32_t> slot_of(n_entries + 2);
+    for (int oct = 0; oct < 8; ++oct) {
+        const float4* L = oct8.data() + (size_t)oct * stride;
+        uint32_t acc = 0;
+        for (uint32_t k = 0; k <= n_entries; ++k) {
+            slot_of[k] = acc;
+            const uint32_t meta = fbits(L[2 * (size_t)k].w);
+            acc += (meta < (1u << 30) || meta == RTB_META_END) ? 1u : 2u;
+        }
+        if (oct == 0) {
+            out.n_slots = acc;
+            out.slots.assign(8 * (size_t)acc, make_uint4(0u, 0u, 0u, RTB_META_END));
+        }
+        uint4* S = out.slots.data() + (size_t)oct * out.n_slots;
+        for (uint32_t k = 0; k <= n_entries; ++k) {
+            const float4 f0 = L[2 * (size_t)k], f1 = L[2 * (size_t)k + 1];
+            const uint32_t meta = fbits(f0.w);
+            uint4& s0 = S[slot_of[k]];
+            if (meta == RTB_META_END) {
+                s0 = make_uint4(0u, 0u, 0u, RTB_META_END);
+            } else if (meta < (1u << 30)) {
+                const float e[3] = {f0.x, f0.y, f0.z}, x[3] = {f1.x, f1.y, f1.z};
+                uint32_t w[3];
+                for (int a = 0; a < 3; ++a) {
+                    const bool neg = ((oct >> a) & 1) != 0;  // entry = max plane, exit = min plane
+                    const double ne = ((double)e[a] - out.center[a]) / out.scale[a];
+                    const double nx = ((double)x[a] - out.center[a]) / out.scale[a];
+                    // outwards: the entry plane moves against the direction of travel, the exit plane along it
+                    const __half he = neg ? __float2half_ru((float)std::nextafter((float)ne, INFINITY))
+                                          : __float2half_rd((float)std::nextafter((float)ne, -INFINITY));
+                    const __half hx = neg ? __float2half_rd((float)std::nextafter((float)nx, -INFINITY))
+                                          : __float2half_ru((float)std::nextafter((float)nx, INFINITY));
+                    w[a] = half_bits(he) | (half_bits(hx) << 16);
+                }
+                s0 = make_uint4(w[0], w[1], w[2], slot_of[meta]);  // skip link: entry index -> slot index
+            } else {
+                uint4& s1 = S[slot_of[k] + 1];
+                s0 = make_uint4(fbits(f0.x), fbits(f0.y), fbits(f0.z), meta);
+                if ((meta >> 30) == KIND_QUAD) s1 = make_uint4(fbits(f1.x), 0u, 0u, fbits(f1.w) | 0x80000000u);
+                else                            s1 = make_uint4(fbits(f1.x), fbits(f1.y), fbits(f1.z), fbits(-std::fabs(f1.w)) | 0x80000000u);
+            }
+        }
+    }
+}
+
 static void scene_free(RtbScene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
@@ -606,6 +700,7 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
         for (int oct = 0; oct < 8; ++oct)
             emit_layout(desc, size, quad_slot, oct, mode == 1, oct_nodes[mode].data() + (size_t)oct * oct_stride);
     }
+    PackedLayout packed;
     {  // mode 2: the library's own SAH partition of the objects the host's tree references
         SahTree sah;
         rc = sah_tree_build(desc, size, sah);
@@ -614,6 +709,11 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
         const size_t sah_stride = 2 * ((size_t)n_tree_sah + 1);
         oct_nodes[2].assign(8 * sah_stride, sentinel);
         for (int oct = 0; oct < 8; ++oct) sah_emit(desc, sah, quad_slot, oct, oct_nodes[2].data() + (size_t)oct * sah_stride);
+        // mode 3 (SAH16): the same layouts packed, when one octant fits in shared memory (else SAH16 renders as SAH)
+        if (n_tree_sah > 0 && ((size_t)n_tree_sah + 1) * 32u <= 2 * megakernel_max_smem_nodes_bytes()) {
+            pack_layout(oct_nodes[2], n_tree_sah, packed);
+            if ((size_t)packed.n_slots * 16u > megakernel_max_smem_nodes_bytes()) packed = PackedLayout{};
+        }
     }
 
     RtbScene* sc = new (std::nothrow) RtbScene();
@@ -687,6 +787,13 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     if (rc == RTB_OK) rc = upload(sc, oct_nodes[0], &sc->dev.oct_nodes[0]);
     if (rc == RTB_OK) rc = upload(sc, oct_nodes[1], &sc->dev.oct_nodes[1]);
     if (rc == RTB_OK) rc = upload(sc, oct_nodes[2], &sc->dev.oct_nodes[2]);
+    if (rc == RTB_OK) rc = upload(sc, packed.slots, &sc->dev.pk_nodes);
+    sc->dev.pk_slots = packed.n_slots;
+    for (int a = 0; a < 3; ++a) {
+        sc->dev.pk_center[a] = packed.center[a];
+        sc->dev.pk_scale[a] = packed.scale[a];
+        sc->dev.pk_inv_scale[a] = 1.0f / packed.scale[a];
+    }
     if (rc == RTB_OK) rc = upload(sc, prims, &sc->dev.prims);
     if (rc == RTB_OK) rc = upload(sc, obj_class, &sc->dev.object_class);
     if (rc == RTB_OK) rc = upload(sc, obj_mat, &sc->dev.object_material);
@@ -753,6 +860,41 @@ extern "C" int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, u
     return RTB_OK;
 }
 
+extern "C" int rtb_debug_packed_layout(const RtbSceneDesc* desc, uint32_t octant, uint32_t* out_slots,
+                                       uint32_t* n_slots_out, float center_out[3], float scale_out[3]) {
+    int rc = validate_desc(desc);
+    if (rc != RTB_OK) return rc;
+    if (octant > 7 || !n_slots_out) return fail(RTB_ERR_INVALID_ARGUMENT, "bad octant / n_slots_out");
+    std::vector<uint32_t> size;
+    uint32_t depth = 0;
+    rc = tree_sizes(desc, size, &depth);
+    if (rc != RTB_OK) return rc;
+    std::vector<uint32_t> quad_slot(desc->n_hittables, 0);
+    std::vector<DevQuad> table;
+    for (uint32_t i = 0; i < desc->n_hittables; ++i)
+        if (desc->hittables[i].type != RTB_HITTABLE_SPHERE) quad_slot[i] = append_complex(table, desc->hittables[i]);
+    SahTree sah;
+    rc = sah_tree_build(desc, size, sah);
+    if (rc != RTB_OK) return rc;
+    const uint32_t n = sah.layout_nodes;
+    if (n == 0 || ((size_t)n + 1) * 32u > 2 * megakernel_max_smem_nodes_bytes())
+        return fail(RTB_ERR_UNSUPPORTED, "scene too large for the packed layout");
+    const size_t stride = 2 * ((size_t)n + 1);
+    std::vector<float4> oct8(8 * stride, mkf4(0.0f, 0.0f, 0.0f, bits(RTB_META_END)));
+    for (int oct = 0; oct < 8; ++oct) sah_emit(desc, sah, quad_slot, oct, oct8.data() + (size_t)oct * stride);
+    PackedLayout packed;
+    pack_layout(oct8, n, packed);
+    if ((size_t)packed.n_slots * 16u > megakernel_max_smem_nodes_bytes())
+        return fail(RTB_ERR_UNSUPPORTED, "scene too large for the packed layout");
+    *n_slots_out = packed.n_slots;
+    for (int a = 0; a < 3; ++a) {
+        if (center_out) center_out[a] = packed.center[a];
+        if (scale_out) scale_out[a] = packed.scale[a];
+    }
+    if (out_slots) std::memcpy(out_slots, packed.slots.data() + (size_t)octant * packed.n_slots, (size_t)packed.n_slots * 16u);
+    return RTB_OK;
+}
+
 extern "C" int rtb_scene_destroy(RtbScene* scene) {
     if (!scene) return RTB_OK;
     // A render in flight on this scene (rtb_render_async's worker, or another thread's rtb_render) holds the mutex:
@@ -767,8 +909,9 @@ extern "C" int rtb_scene_destroy(RtbScene* scene) {
 extern "C" int rtb_trace_rays(RtbScene* scene, const RtbRay* rays, uint64_t n, uint32_t traversal, RtbHit* hits_out) {
     if (!scene) return fail(RTB_ERR_INVALID_ARGUMENT, "scene is NULL");
     if (n && (!rays || !hits_out)) return fail(RTB_ERR_INVALID_ARGUMENT, "rays/hits_out is NULL");
-    if (traversal > RTB_TRAVERSAL_SAH) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", traversal);
+    if (traversal > RTB_TRAVERSAL_SAH16) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", traversal);
     if (n == 0) return RTB_OK;
+    if (traversal == RTB_TRAVERSAL_SAH16 && !scene->dev.pk_nodes) traversal = RTB_TRAVERSAL_SAH;  // too large to pack
     std::lock_guard<std::mutex> lock(scene->mutex);
     RTB_CUDA(cudaSetDevice(scene->device));
     RtbRay* d_rays = nullptr;
@@ -811,7 +954,7 @@ static int check_render_args(RtbScene* scene, const RtbCamera* cam, const RtbRen
     if (opt->tile_world > 0 && opt->tile_rank >= opt->tile_world) return fail(RTB_ERR_INVALID_ARGUMENT, "tile_rank >= tile_world");
     if (opt->integrator != RTB_INTEGRATOR_MEGAKERNEL && opt->integrator != RTB_INTEGRATOR_WAVEFRONT)
         return fail(RTB_ERR_INVALID_ARGUMENT, "unknown integrator %u", opt->integrator);
-    if (opt->traversal > RTB_TRAVERSAL_SAH) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", opt->traversal);
+    if (opt->traversal > RTB_TRAVERSAL_SAH16) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", opt->traversal);
     if (cam->background_mode > RTB_BACKGROUND_SKY) return fail(RTB_ERR_INVALID_ARGUMENT, "unknown background mode");
     return RTB_OK;
 }
@@ -853,6 +996,7 @@ static int render_enqueue(RtbScene* scene, const RtbCamera* cam, const RtbRender
     p.tile_rank = opt->tile_rank;
     p.tile_world = opt->tile_world ? opt->tile_world : 1u;
     p.ordered = opt->traversal;
+    if (p.ordered == RTB_TRAVERSAL_SAH16 && !scene->dev.pk_nodes) p.ordered = RTB_TRAVERSAL_SAH;  // too large to pack
     const bool count_work = (opt->flags & RTB_FLAG_COUNT_WORK) != 0;
     p.counters = count_work ? scene->d_counters : nullptr;
     if (opt->integrator == RTB_INTEGRATOR_WAVEFRONT) {

@@ -14,6 +14,7 @@
 // square root are IEEE (nvcc defaults -prec-div=true -prec-sqrt=true, no --use_fast_math).
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -69,6 +70,18 @@ struct DevScene {
     // its box: h + 3(n - h) - 2 entries for n objects of which h are huge.
     const float4* oct_nodes[3];
     uint32_t oct_n_nodes[3];
+    // RTB_TRAVERSAL_SAH16: the mode-2 tree packed into 16-byte SLOTS, [octant][pk_slots] (see traverse_packed):
+    //   box node (1 slot)   {half2(entry.x, exit.x), half2(entry.y, exit.y), half2(entry.z, exit.z), skip slot}
+    //                       planes in the layout's own normalised frame n = (x - pk_center) * pk_inv_scale, |n| <= 1,
+    //                       rounded OUTWARDS to binary16 on the host;
+    //   leaf      (2 slots) {center1.xyz, kind|object} {center_vec.xyz, -radius}   (f32, world frame; complex objects:
+    //                       {.., kind|object} {bits(subtype), 0, 0, 0x80000000 | quad slot}) — the last word of a leaf
+    //                       always has bit 31 set, so "word 3 < 2^30" identifies exactly the box nodes' skip links;
+    //   end sentinel (1 slot) word 3 = RTB_META_END.
+    // NULL when the packed layout would not fit in shared memory (then SAH16 renders as SAH).
+    const uint4* pk_nodes;
+    uint32_t pk_slots;  // slots per octant, sentinel included
+    float pk_center[3], pk_inv_scale[3], pk_scale[3];
     // 4 per object: the leaf record {center1, kind|object}, {center_vec, radius} and the object's material
     // record {m0, m1} inlined (the reference stores Material by value in every Hittable anyway).
     const float4* prims;
@@ -470,6 +483,149 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
                 }
             }
             i = i + kStep;
+        }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------ RTB_TRAVERSAL_SAH16: packed half2 box tests
+// The box test of the library's own SAH tree only has to be CONSERVATIVE (never reject a box the ray enters before
+// its current nearest hit): leaves keep the reference's f32 arithmetic, so every hit value stays bit-identical.  That
+// freedom is spent on the two things ncu shows wf_extend is bound by (profiles/r2a_*: l1tex 82-88 % busy on the node
+// fetches, 18 issue slots per visit): a box node is ONE 16-byte slot (one LDS.128 instead of two) and the slab test is
+// three HFMA2 on (entry, exit) plane pairs, two packed max and one packed compare — 12 instructions per visit.
+//
+// Per axis, with planes e (entry) and x (exit) in the normalised frame and the ray's own per-axis constants
+//   (t_entry, -t_exit) = (e, x) * (I_lo, I_hi) + (N_lo, N_hi)            one HFMA2
+//   I_lo =  inv * (1 - k)    N_lo =  nod * (1 - k) - E
+//   I_hi = -inv * (1 + k)    N_hi = -nod * (1 + k) - E       inv = 1 / d_n,  nod = -o_n * inv  (f32, then rounded to f16)
+// k = 1.01 * 2^-11 covers the final rounding of the HFMA2 (|t| only ever shrinks for the entry and grows for the exit),
+// E = 1.01 * 2^-11 * (|inv| + |nod|) covers the roundings of I and N themselves (|e|, |x| <= 1).  A ray whose
+// |inv| + |nod| would not fit binary16 is scaled as a whole by a power of two (t' = sigma * t: roundings are relative, so
+// nothing else changes); an axis with d = 0 (1/d infinite) or a NaN term constrains nothing.
+// So computed t_entry <= true t_entry and computed t_exit >= true t_exit, for every ray: the walk visits a SUPERSET
+// of the nodes an exact test on the same boxes would.  In space the slack is ~2^-11 (1 + |o_n|) of the scene's
+// half-extent plus 2^-11 of the distance travelled: on Book-1 ~0.02 units against leaf boxes of 0.4-1.0.
+struct PackedRay {
+    uint32_t ix, iy, iz, nx, ny, nz;  // half2 bit patterns (lo half: entry, hi half: exit)
+    float sigma;                      // power of two all t values of this ray are scaled by to fit binary16
+};
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2_bits(__half lo, __half hi) {
+    const __half2 h = __halves2half2(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+// inv = 1 / d_n and nod = -o_n / d_n of one axis in the layout's normalised frame, and |inv| + |nod|
+__device__ __forceinline__ void packed_axis_terms(float o, float d, float center, float inv_scale, float scale, float& inv,
+                                                  float& nod, float& mag) {
+    const float on = (o - center) * inv_scale;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));  // binary16 precision is all the test keeps
+    inv = scale * r;                                       // 1 / d_n with d_n = d * inv_scale
+    nod = -(on * inv);
+    mag = fabsf(inv) + fabsf(nod);
+}
+__device__ __forceinline__ void packed_axis_pack(float inv, float nod, float mag, float sigma, uint32_t& I, uint32_t& N) {
+    if (!(mag < 3.0e38f)) {  // d = 0 (1/d = inf) or NaN (0 * inf): this axis constrains nothing
+        I = 0u;
+        N = 0xfc00fc00u;     // (-inf, -inf): t_entry = -inf, t_exit = +inf
+        return;
+    }
+    const float k = 1.01f / 2048.0f;
+    const float E = mag * (1.01f / 2048.0f) + 1e-7f;
+    I = h2_bits(__float2half_rn(sigma * (inv * (1.0f - k))), __float2half_rn(sigma * -(inv * (1.0f + k))));
+    N = h2_bits(__float2half_rn(sigma * (nod * (1.0f - k) - E)), __float2half_rn(sigma * (-(nod * (1.0f + k)) - E)));
+}
+__device__ __forceinline__ PackedRay packed_ray_setup(const DevScene& sc, float3 o, float3 d) {
+    PackedRay pr;
+    float ix, iy, iz, nx, ny, nz, mx, my, mz;
+    packed_axis_terms(o.x, d.x, sc.pk_center[0], sc.pk_inv_scale[0], sc.pk_scale[0], ix, nx, mx);
+    packed_axis_terms(o.y, d.y, sc.pk_center[1], sc.pk_inv_scale[1], sc.pk_scale[1], iy, ny, my);
+    packed_axis_terms(o.z, d.z, sc.pk_center[2], sc.pk_inv_scale[2], sc.pk_scale[2], iz, nz, mz);
+    // binary16 holds |x| < 65504: a ray far from the scene (|o_n| large: a bounce off the ground sphere thousands of
+    // units away) or nearly parallel to an axis has |inv| + |nod| beyond that.  Rounding errors are relative, so the
+    // whole ray is simply scaled by a power of two: t' = sigma * t, with the interval (t_min, t_max) scaled alike.
+    float m = 0.0f;
+    if (mx < 3.0e38f) m = fmaxf(m, mx);
+    if (my < 3.0e38f) m = fmaxf(m, my);
+    if (mz < 3.0e38f) m = fmaxf(m, mz);
+    const int e = (int)(__float_as_uint(m) >> 23) - 127;                 // floor(log2 m), m >= 0 finite
+    const int kk = e > 12 ? (e - 12 > 120 ? 120 : e - 12) : 0;           // keep sigma * m < 2^13
+    pr.sigma = __uint_as_float((uint32_t)(127 - kk) << 23);
+    packed_axis_pack(ix, nx, mx, pr.sigma, pr.ix, pr.nx);
+    packed_axis_pack(iy, ny, my, pr.sigma, pr.iy, pr.ny);
+    packed_axis_pack(iz, nz, mz, pr.sigma, pr.iz, pr.nz);
+    return pr;
+}
+// (sigma * t_min rounded down, -(sigma * t_max rounded up)) as half2: the fourth operand of the packed max
+__device__ __forceinline__ __half2 packed_interval(float t_min, float t_max, float sigma) {
+    return __halves2half2(__float2half_rd(sigma * t_min), __hneg(__float2half_ru(sigma * t_max)));
+}
+
+// Walk over one octant's packed layout.  SMEM: `smem_base` is the shared-window address of the staged copy, whose skip
+// links are addresses (rewritten while staging); otherwise `slots` is the octant's array and the links are slot indices.
+template <bool COUNT, bool QUADS, bool SMEM>
+__device__ __forceinline__ Nearest traverse_packed(const uint4* __restrict__ slots, const DevQuad* __restrict__ quads,
+                                                   float3 o, float3 d, float time, const PackedRay& pr, float t_min,
+                                                   float t_max, uint32_t& n_box, uint32_t& n_obj,
+                                                   uint32_t smem_base = 0u, RngKey key = RngKey{},
+                                                   uint32_t segment = 1u) {
+    Nearest best;
+    best.t = t_max;
+    best.node = 0xffffffffu;
+    const float a = length_squared(d);
+    const __half2 ix = as_h2(pr.ix), iy = as_h2(pr.iy), iz = as_h2(pr.iz);
+    const __half2 nx = as_h2(pr.nx), ny = as_h2(pr.ny), nz = as_h2(pr.nz);
+    __half2 K = packed_interval(t_min, t_max, pr.sigma);
+    constexpr uint32_t kStep = SMEM ? 16u : 1u;
+    uint32_t i = SMEM ? smem_base : 0u;
+    for (;;) {
+        uint4 n;
+        if (SMEM) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(n.x), "=r"(n.y), "=r"(n.z), "=r"(n.w) : "r"(i));
+        } else {
+            n = slots[i];
+        }
+        if (n.w < (1u << 30)) {  // box node: word 3 is the skip link
+            if (COUNT) ++n_box;
+            const __half2 tx = __hfma2(as_h2(n.x), ix, nx);
+            const __half2 ty = __hfma2(as_h2(n.y), iy, ny);
+            const __half2 tz = __hfma2(as_h2(n.z), iz, nz);
+            const __half2 r = __hmax2(__hmax2(tx, ty), __hmax2(tz, K));  // (t_entry, -t_exit); NaN operands are ignored
+            const bool miss = __hge(__high2half(r), __hneg(__low2half(r)));  // t_exit <= t_entry
+            i = miss ? n.w : i + kStep;
+        } else {
+            if (n.w == RTB_META_END) break;
+            if (COUNT) ++n_obj;
+            uint4 m;
+            if (SMEM) {
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(i));
+            } else {
+                m = slots[i + 1u];
+            }
+            const uint32_t kind = n.w >> 30;
+            bool hit;
+            float root;
+            if (!QUADS || kind != KIND_QUAD) {
+                const float3 c1 = f3(__uint_as_float(n.x), __uint_as_float(n.y), __uint_as_float(n.z));
+                const float3 cv = f3(__uint_as_float(m.x), __uint_as_float(m.y), __uint_as_float(m.z));
+                const float3 center = (kind == KIND_MOVING_SPHERE) ? c1 + splat3(time) * cv : c1;
+                // word 3 holds -radius (bit 31 marks a leaf's second slot); only radius^2 is used here
+                hit = sphere_root_a(o, d, a, center, __uint_as_float(m.w), t_min, best.t, root);
+            } else {
+                DRay r;
+                r.o = o;
+                r.d = d;
+                r.time = time;
+                const float4 f1 = make_float4(__uint_as_float(m.x), 0.0f, 0.0f, __uint_as_float(m.w & 0x7fffffffu));
+                hit = complex_root(r, quads, f1, t_min, best.t, root, key, segment, n.w & RTB_META_INDEX_MASK);
+            }
+            if (hit) {
+                best.t = root;
+                best.node = n.w & RTB_META_INDEX_MASK;
+                K = packed_interval(t_min, root, pr.sigma);
+            }
+            i = i + 2u * kStep;
         }
     }
     return best;

@@ -55,7 +55,12 @@ __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderPar
             for (;;) {
                 if (COUNT) ++n_rays;
                 Nearest best;
-                if (ORDERED) {
+                if (ORDERED && P.ordered == 3u) {  // RTB_TRAVERSAL_SAH16: packed half2 box nodes
+                    const uint4* slots = P.scene.pk_nodes + (size_t)ray_octant_of_direction(ray.d) * P.scene.pk_slots;
+                    const PackedRay pr = packed_ray_setup(P.scene, ray.o, ray.d);
+                    best = traverse_packed<COUNT, QUADS, false>(slots, P.scene.quads, ray.o, ray.d, ray.time, pr, 0.001f,
+                                                                __int_as_float(0x7f800000), n_box, n_obj, 0u, key, segment);
+                } else if (ORDERED) {
                     const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
                     const float4* oct =
                         P.scene.oct_nodes[P.ordered] + (size_t)ray_octant(ix, iy, iz) * 2u * (P.scene.oct_n_nodes[P.ordered] + 1u);
@@ -188,7 +193,12 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     qkey.pixel = (uint32_t)i;
     qkey.sample = 0u;
     Nearest best;
-    if (ORDERED) {
+    if (ORDERED && layout == 3u) {
+        const uint4* slots = scene.pk_nodes + (size_t)ray_octant_of_direction(r.d) * scene.pk_slots;
+        const PackedRay pr = packed_ray_setup(scene, r.o, r.d);
+        best = traverse_packed<true, QUADS, false>(slots, scene.quads, r.o, r.d, r.time, pr, rr.t_min, rr.t_max, n_box,
+                                                   n_obj, 0u, qkey, 1u);
+    } else if (ORDERED) {
         const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
         const float4* oct = scene.oct_nodes[layout] + (size_t)ray_octant(ix, iy, iz) * 2u * (scene.oct_n_nodes[layout] + 1u);
         if (layout == 2u)

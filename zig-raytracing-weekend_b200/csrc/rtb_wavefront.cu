@@ -58,6 +58,9 @@ constexpr uint32_t kExtendThreads = RTB_EXTEND_THREADS;
 #ifndef RTB_SHADE_MINBLOCKS
 #define RTB_SHADE_MINBLOCKS 5
 #endif
+#ifndef RTB_EXTEND_MINBLOCKS
+#define RTB_EXTEND_MINBLOCKS 3
+#endif
 
 // 32-byte records everywhere (= one DRAM sector), because the shade kernel GATHERS them: ncu (r1e) showed
 // it DRAM-bound at ~50 % of HBM peak fetching 16 B pieces out of separate arrays, two sectors per 32 B used.
@@ -210,11 +213,16 @@ __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
 
 // One thread per ray, plain node loop over the octant's layout; the result goes to the hit queue of
 // the hit object's shading class.
-// FMA: the layout is the library's own padded SAH tree (mode 2), whose slab test may use one FMA per plane.
-template <bool SMEM_NODES, bool COUNT, bool QUADS, bool FMA>
-__global__ void __launch_bounds__(kExtendThreads) wf_extend(const WfParams P) {
+// SLAB = how a box node is tested: kSlabExact the reference's arithmetic on pre-swapped planes (layouts 0 and 1),
+// kSlabFma one FMA per plane on the library's own padded SAH tree (layout 2), kSlabPacked the 16-byte half2 nodes of
+// RTB_TRAVERSAL_SAH16 (traverse_packed).
+enum : int { kSlabExact = 0, kSlabFma = 1, kSlabPacked = 2 };
+template <bool SMEM_NODES, bool COUNT, bool QUADS, int SLAB>
+__global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_extend(const WfParams P) {
     __shared__ ChunkMap map;
-    const uint32_t n_nodes = P.R.scene.oct_n_nodes[P.R.ordered];
+    constexpr bool PACKED = SLAB == kSlabPacked;
+    const uint32_t layout = PACKED ? 2u : P.R.ordered;
+    const uint32_t n_nodes = P.R.scene.oct_n_nodes[layout];
     chunk_map_init(map, P.count_in, kOctants, kExtendThreads);
     // Bins nobody reads during this kernel: the ray bins this bounce's shade kernel will push into and
     // the hit bins of the next bounce.
@@ -228,8 +236,10 @@ __global__ void __launch_bounds__(kExtendThreads) wf_extend(const WfParams P) {
         P.survivors[P.segment - 1u] = total;
     }
     const uint32_t total_chunks = map.first_chunk[kBins];
-    const size_t oct_stride = 2u * ((size_t)n_nodes + 1u);
-    const float4* __restrict__ layouts = P.R.scene.oct_nodes[P.R.ordered];
+    // 16-byte units per octant: 2 per node (+ sentinel) for the float4 layouts, pk_slots for the packed one
+    const size_t oct_stride = PACKED ? (size_t)P.R.scene.pk_slots : 2u * ((size_t)n_nodes + 1u);
+    const float4* __restrict__ layouts =
+        PACKED ? reinterpret_cast<const float4*>(P.R.scene.pk_nodes) : P.R.scene.oct_nodes[layout];
     uint32_t staged = kOctants;  // octant whose layout is in shared memory
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(rtb_smem_nodes) + P.zero;
     uint32_t n_box = 0, n_obj = 0, n_rays = 0;
@@ -251,7 +261,11 @@ __global__ void __launch_bounds__(kExtendThreads) wf_extend(const WfParams P) {
             for (uint32_t i = threadIdx.x; i < (uint32_t)oct_stride; i += blockDim.x) {
                 float4 v = nodes[i];
                 const uint32_t meta = __float_as_uint(v.w);
-                if ((i & 1u) == 0u && meta < (1u << 30)) v.w = __uint_as_float(smem_base + meta * 32u);
+                if (PACKED) {  // every slot: word 3 < 2^30 <=> box node (leaves set bit 30/31 in both of their slots)
+                    if (meta < (1u << 30)) v.w = __uint_as_float(smem_base + meta * 16u);
+                } else if ((i & 1u) == 0u && meta < (1u << 30)) {
+                    v.w = __uint_as_float(smem_base + meta * 32u);
+                }
                 rtb_smem_nodes[i] = v;
             }
             __syncthreads();
@@ -274,9 +288,17 @@ __global__ void __launch_bounds__(kExtendThreads) wf_extend(const WfParams P) {
                 slot_pixel(P.R, slot % P.slots_per_sample, key.pixel);
                 key.sample = P.batch_begin + slot / P.slots_per_sample;
             }
-            const Nearest best = traverse_octant<COUNT, QUADS, SMEM_NODES, FMA>(
-                nodes, P.R.scene.quads, o, d, a.w, 1.0f / d.x, 1.0f / d.y, 1.0f / d.z, 0.001f, __int_as_float(0x7f800000),
-                n_box, n_obj, smem_base, key, P.segment);
+            Nearest best;
+            if (PACKED) {
+                const PackedRay pr = packed_ray_setup(P.R.scene, o, d);
+                best = traverse_packed<COUNT, QUADS, SMEM_NODES>(reinterpret_cast<const uint4*>(nodes), P.R.scene.quads, o,
+                                                                 d, a.w, pr, 0.001f, __int_as_float(0x7f800000), n_box,
+                                                                 n_obj, smem_base, key, P.segment);
+            } else {
+                best = traverse_octant<COUNT, QUADS, SMEM_NODES, SLAB == kSlabFma>(
+                    nodes, P.R.scene.quads, o, d, a.w, 1.0f / d.x, 1.0f / d.y, 1.0f / d.z, 0.001f,
+                    __int_as_float(0x7f800000), n_box, n_obj, smem_base, key, P.segment);
+            }
             if (best.node != 0xffffffffu) cls = P.R.scene.object_class[best.node];
             entry = make_uint4((uint32_t)at, __float_as_uint(best.t), best.node, __float_as_uint(b.w));
         }
@@ -350,13 +372,15 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
 // step for < 1 % of the work).  wf_tail finishes every path that is still alive in ONE launch: a thread takes one ray of
 // the current queue and runs the rest of that path like the megakernel does — same traversal, same shading, same Philox
 // streams, so the result is bit-identical whichever bounce the switch happens at.
-template <bool COUNT, bool QUADS, bool FMA>
+template <bool COUNT, bool QUADS, int SLAB>
 __global__ void __launch_bounds__(256) wf_tail(const WfParams P) {
     __shared__ ChunkMap map;
     chunk_map_init(map, P.count_in, kOctants);
+    constexpr bool PACKED = SLAB == kSlabPacked;
     const uint32_t total_chunks = map.first_chunk[kBins];
-    const size_t oct_stride = 2u * ((size_t)P.R.scene.oct_n_nodes[P.R.ordered] + 1u);
-    const float4* __restrict__ layouts = P.R.scene.oct_nodes[P.R.ordered];
+    const size_t oct_stride = PACKED ? (size_t)P.R.scene.pk_slots : 2u * ((size_t)P.R.scene.oct_n_nodes[P.R.ordered] + 1u);
+    const float4* __restrict__ layouts =
+        PACKED ? reinterpret_cast<const float4*>(P.R.scene.pk_nodes) : P.R.scene.oct_nodes[P.R.ordered];
     uint32_t n_rays = 0, n_box = 0, n_obj = 0, n_hits = 0;
     for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
         uint32_t bin = 0;
@@ -382,11 +406,20 @@ __global__ void __launch_bounds__(256) wf_tail(const WfParams P) {
         uint32_t segment = P.segment;
         for (;;) {
             if (COUNT) ++n_rays;
-            const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
-            const float4* __restrict__ nodes = layouts + (size_t)ray_octant(ix, iy, iz) * oct_stride;
-            const Nearest best = traverse_octant<COUNT, QUADS, false, FMA>(nodes, P.R.scene.quads, ray.o, ray.d, ray.time, ix,
-                                                                          iy, iz, 0.001f, __int_as_float(0x7f800000),
-                                                                          n_box, n_obj, 0u, key, segment);
+            Nearest best;
+            if (PACKED) {
+                const uint4* __restrict__ slots =
+                    reinterpret_cast<const uint4*>(layouts) + (size_t)ray_octant_of_direction(ray.d) * oct_stride;
+                const PackedRay pr = packed_ray_setup(P.R.scene, ray.o, ray.d);
+                best = traverse_packed<COUNT, QUADS, false>(slots, P.R.scene.quads, ray.o, ray.d, ray.time, pr, 0.001f,
+                                                            __int_as_float(0x7f800000), n_box, n_obj, 0u, key, segment);
+            } else {
+                const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
+                const float4* __restrict__ nodes = layouts + (size_t)ray_octant(ix, iy, iz) * oct_stride;
+                best = traverse_octant<COUNT, QUADS, false, SLAB == kSlabFma>(nodes, P.R.scene.quads, ray.o, ray.d, ray.time,
+                                                                             ix, iy, iz, 0.001f, __int_as_float(0x7f800000),
+                                                                             n_box, n_obj, 0u, key, segment);
+            }
             if (best.node == 0xffffffffu) {
                 L = L + T * miss_color(P.R.cam, ray);
                 break;
@@ -495,25 +528,30 @@ static cudaError_t lane_reserve(WfLane* ln, size_t capacity) {
     return cudaSuccess;
 }
 
-template <bool COUNT, bool QUADS, bool FMA>
-static cudaError_t wf_launch_extend_fma(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
+// Bytes of one octant's layout as the extend kernel stages it.
+static size_t wf_layout_bytes(const DevScene& sc, uint32_t ordered) {
+    return ordered == 3u ? (size_t)sc.pk_slots * 16u : ((size_t)sc.oct_n_nodes[ordered] + 1u) * 32u;
+}
+template <bool COUNT, bool QUADS, int SLAB>
+static cudaError_t wf_launch_extend_slab(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
     if (smem_nodes) {
-        const size_t smem = ((size_t)P.R.scene.oct_n_nodes[P.R.ordered] + 1u) * 32u;
-        auto k = wf_extend<true, COUNT, QUADS, FMA>;
+        const size_t smem = wf_layout_bytes(P.R.scene, P.R.ordered);
+        auto k = wf_extend<true, COUNT, QUADS, SLAB>;
         if (smem > 40u * 1024u) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
         k<<<grid, kExtendThreads, smem, stream>>>(P);
     } else {
-        wf_extend<false, COUNT, QUADS, FMA><<<grid, kExtendThreads, 0, stream>>>(P);
+        wf_extend<false, COUNT, QUADS, SLAB><<<grid, kExtendThreads, 0, stream>>>(P);
     }
     return cudaGetLastError();
 }
 template <bool COUNT, bool QUADS>
 static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
-    return P.R.ordered == 2u ? wf_launch_extend_fma<COUNT, QUADS, true>(P, smem_nodes, grid, stream)
-                             : wf_launch_extend_fma<COUNT, QUADS, false>(P, smem_nodes, grid, stream);
+    if (P.R.ordered == 3u) return wf_launch_extend_slab<COUNT, QUADS, kSlabPacked>(P, smem_nodes, grid, stream);
+    return P.R.ordered == 2u ? wf_launch_extend_slab<COUNT, QUADS, kSlabFma>(P, smem_nodes, grid, stream)
+                             : wf_launch_extend_slab<COUNT, QUADS, kSlabExact>(P, smem_nodes, grid, stream);
 }
 
 // Batches of ~8 M paths are pipelined over kLanes streams.  After the first ~10 bounces a batch is a
@@ -594,8 +632,7 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         if (e != cudaSuccess) return e;
     }
 
-    const bool smem_nodes =
-        p.scene.n_nodes > 0 && ((size_t)p.scene.oct_n_nodes[p.ordered] + 1u) * 32u <= megakernel_max_smem_nodes_bytes();
+    const bool smem_nodes = p.scene.n_nodes > 0 && wf_layout_bytes(p.scene, p.ordered) <= megakernel_max_smem_nodes_bytes();
     const bool quads = p.scene.has_quads != 0u;
     const uint32_t max_grid = (uint32_t)st->sm_count * 8u;
 
@@ -661,8 +698,9 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
                 const uint32_t grid_t = (uint32_t)st->sm_count * 4u;
 #define RTB_TAIL(C, Q)                                                                         \
     do {                                                                                       \
-        if (p.ordered == 2u) wf_tail<C, Q, true><<<grid_t, 256, 0, ln.stream>>>(P);            \
-        else                 wf_tail<C, Q, false><<<grid_t, 256, 0, ln.stream>>>(P);           \
+        if (p.ordered == 3u)      wf_tail<C, Q, kSlabPacked><<<grid_t, 256, 0, ln.stream>>>(P); \
+        else if (p.ordered == 2u) wf_tail<C, Q, kSlabFma><<<grid_t, 256, 0, ln.stream>>>(P);    \
+        else                      wf_tail<C, Q, kSlabExact><<<grid_t, 256, 0, ln.stream>>>(P);  \
     } while (0)
                 if (count_work) { if (quads) RTB_TAIL(true, true); else RTB_TAIL(true, false); }
                 else            { if (quads) RTB_TAIL(false, true); else RTB_TAIL(false, false); }

@@ -32,21 +32,56 @@ class Partition:
     total_samples: int  # samples per pixel in the combined frame
 
 
-def plan(mode: str, rank: int, world: int, samples: int, sample_base: int = 0, weak: bool = False) -> Partition:
+def split_samples(total: int, world: int, weights=None):
+    """Split `total` samples over `world` ranks: equal shares, or proportional to `weights` (e.g. the rate every rank
+    showed in warm-up renders — a slower GPU then gets fewer samples instead of making the others wait at the
+    exchange).  Largest-remainder rounding, at least one sample per rank; deterministic, so every rank computes the
+    same table from the same (all-gathered) weights.  Returns the per-rank counts."""
+    if total < world:
+        raise ValueError(f"{total} samples cannot be shared by {world} ranks")
+    if weights is None:
+        base, rem = divmod(total, world)
+        return [base + (1 if r < rem else 0) for r in range(world)]
+    if len(weights) != world or any(not (w > 0.0) for w in weights):
+        raise ValueError("weights must be one positive number per rank")
+    s = float(sum(weights))
+    ideal = [total * w / s for w in weights]
+    counts = [max(1, int(x)) for x in ideal]
+    # hand out / take back the difference by largest (smallest) remainder
+    order = sorted(range(world), key=lambda r: ideal[r] - int(ideal[r]), reverse=True)
+    k = 0
+    while sum(counts) < total:
+        counts[order[k % world]] += 1
+        k += 1
+    k = 0
+    while sum(counts) > total:
+        r = order[-1 - (k % world)]
+        if counts[r] > 1:
+            counts[r] -= 1
+        k += 1
+    return counts
+
+
+def plan(mode: str, rank: int, world: int, samples: int, sample_base: int = 0, weak: bool = False,
+         weights=None) -> Partition:
     """Partition `samples` samples per pixel over `world` ranks.
 
-    weak=True (sample mode only): every rank renders `samples` samples, so the combined frame holds
-    world*samples per pixel (fixed work per GPU — the bench's weak-scaling workload).
+    weak=True (sample mode only): the combined frame holds world*samples per pixel (fixed work per GPU on average —
+    the bench's weak-scaling workload); otherwise the ranks share `samples`.  weights (sample mode only): per-rank
+    rates for a proportional split (see split_samples); None = equal shares.
     """
     if world < 1 or not (0 <= rank < world):
         raise ValueError("bad rank/world")
     if mode == "samples":
-        if weak:
-            return Partition(mode, rank, world, sample_base + rank * samples, samples, 0, 1, world * samples)
-        base, rem = divmod(samples, world)
-        count = base + (1 if rank < rem else 0)
-        begin = rank * base + min(rank, rem)
-        return Partition(mode, rank, world, sample_base + begin, count, 0, 1, samples)
+        total = world * samples if weak else samples
+        if weak and weights is None:
+            return Partition(mode, rank, world, sample_base + rank * samples, samples, 0, 1, total)
+        if total < world:   # fewer samples than ranks: the trailing ranks get none (callers skip their render)
+            counts = [1 if r < total else 0 for r in range(world)]
+        else:
+            counts = split_samples(total, world, weights)
+        begin = sum(counts[:rank])
+        return Partition(mode, rank, world, sample_base + begin, counts[rank], 0, 1, total)
     if mode == "tiles":
         if weak:
             raise ValueError("weak scaling is defined for the sample partition only")
@@ -56,6 +91,8 @@ def plan(mode: str, rank: int, world: int, samples: int, sample_base: int = 0, w
 
 def apply(part: Partition, options):
     """Write a Partition into an RtbRenderOptions."""
+    if part.sample_count == 0:   # RtbRenderOptions.sample_count == 0 means "the camera's spp", not "nothing"
+        raise ValueError("this rank has no samples to render (more ranks than samples): skip its render call")
     options.sample_begin = part.sample_begin
     options.sample_count = part.sample_count
     options.tile_rank = part.tile_rank
@@ -217,7 +254,7 @@ class PeerExchange:
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)
 
-    def exchange(self, samples_per_pixel: float, stream: int | None = None):
+    def exchange(self, samples_per_pixel: float, stream: int | None = None, n_pixels: int | None = None):
         """barrier -> rtb_exchange_resolve on every rank -> barrier, all on `stream` (raw cudaStream_t; None = torch's
         current stream).  Afterwards rank `root`'s `accum` holds the combined sums (.w = samples_per_pixel) and its
         `rgba` the resolved frame.  NOTE: root's `accum` then holds the COMBINED sums — zero every rank's `accum`
@@ -226,8 +263,11 @@ class PeerExchange:
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         self.barrier(stream)
+        n = self.n_pixels if n_pixels is None else int(n_pixels)   # a frame smaller than the buffers: their first n pixels
+        if not (0 < n <= self.n_pixels):
+            raise ValueError("n_pixels out of range")
         self._check(self._ffi.rtb().rtb_exchange_resolve(self._peers, self.world, self.rank, self.root, self.root_accum,
-                                                         self.root_rgba, self.n_pixels, float(samples_per_pixel),
+                                                         self.root_rgba, n, float(samples_per_pixel),
                                                          self.device, stream), "rtb_exchange_resolve")
         self.barrier(stream)
 
