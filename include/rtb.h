@@ -391,7 +391,9 @@ int rtb_group_destroy(RtbSceneGroup* group);
 int rtb_group_size(const RtbSceneGroup* group, uint32_t* n_devices_out);
 /* Like rtb_render: accum / rgba are HOST buffers of the whole frame; the samples are ADDED to accum and .w is set to
  * sample_begin + sample_count.  options.pixel_* / tile_* must be 0 (the library partitions); integrator, traversal,
- * seed, sample range and flags apply to every device.  stats: sums over the devices, device_ms = the slowest. */
+ * seed, sample range and flags apply to every device.  stats: sums over the devices, device_ms = the slowest.
+ * Starting from a cleared buffer the TILES frame is bit-identical to rtb_render's; sums already in accum stay on the
+ * first device and are added once at the exchange, i.e. in a different float association than sample-by-sample. */
 int rtb_group_render(RtbSceneGroup* group, const RtbCamera* camera, const RtbRenderOptions* options, uint32_t partition,
                      float* accum, uint8_t* rgba, RtbRenderStats* stats);
 

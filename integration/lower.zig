@@ -130,10 +130,10 @@ pub fn lowerMaterial(l: *Lowered, mat: Material) LowerError!u32 {
     return index;
 }
 
-/// A `createBox(a, b, mat)` list (src/objects.zig:510-532): six quads that share one material.  Recovers the two
-/// corners handed to createBox from the quads' q / u / v (sides[0] = front: q = (min.x, min.y, max.z)?  No — HEAD's
-/// createBox emits the z = min face twice and no z = max face, `:520-529`; the corners are the extrema of all q,
-/// q + u, q + v, q + u + v, which is what the library rebuilds the same six quads from).
+/// A `createBox(a, b, mat)` list (src/objects.zig:510-532): six quads that share one material.  The two corners handed
+/// to createBox are recovered as the extrema of the quads' corners (q, q + u, q + v, q + u + v); the library rebuilds
+/// the same six quads from them, in createBox's order — including HEAD's quirk of emitting the z = min face twice and
+/// no z = max face (:520-529), which tests/test_cornell.py pins.
 fn boxCorners(list: objects.HittableList, a: *[3]f32, b: *[3]f32, mat: *Material) LowerError!void {
     if (list.objects.items.len != 6) return LowerError.Unsupported;
     var mn = [3]f32{ std.math.inf(f32), std.math.inf(f32), std.math.inf(f32) };

@@ -35,8 +35,11 @@ def test_group_render_reproduces_the_single_device_frame(pkg, orc):
             # tiles: disjoint pixels -> the very same bits as one device, sums and RGBA8
             t, t_rgba, stt = grp.render(cam, o, partition=pkg.RTB_PARTITION_TILES)
             assert np.array_equal(t, one) and np.array_equal(t_rgba, one_rgba), (devices, integrator)
-            for k in ("n_paths", "n_rays", "n_box_tests", "n_object_tests", "n_hits"):
+            for k in ("n_paths", "n_rays", "n_hits"):
                 assert stt[k] == st1[k], (k, devices)
+            for k in ("n_box_tests", "n_object_tests"):    # SAH16's streaming extend kernel parks leaves: how many
+                # extra nodes a ray visits depends on the rays it shares a warp with — the hits do not
+                assert abs(stt[k] - st1[k]) <= (2e-3 * st1[k] if trav == 3 else 0), (k, devices)
             # samples: the same paths; only the association of the per-pixel float sums differs
             s, s_rgba, sts = grp.render(cam, o, partition=pkg.RTB_PARTITION_SAMPLES)
             assert (s[:, 3] == 9).all() and sts["n_paths"] == st1["n_paths"] and sts["n_rays"] == st1["n_rays"]
@@ -66,7 +69,11 @@ def test_group_render_adds_to_the_callers_buffer_and_checks_arguments(pkg):
                          partition=pkg.RTB_PARTITION_TILES)
     a, rgba, _ = grp.render(cam, pkg.render_options(seed=3, integrator=1, traversal=2, sample_begin=2, sample_count=4),
                             partition=pkg.RTB_PARTITION_TILES, accum=a)
-    assert np.array_equal(a, full) and (rgba[:, 3] == 255).all()
+    # the earlier sums live on the root device, so a tile owned by another device adds (s0+s1) + (s2+..+s5) instead of
+    # the sequential sum: equal up to float association (exact for the root's own tiles and for a cleared buffer)
+    np.testing.assert_allclose(a[:, :3], full[:, :3], rtol=2e-6, atol=1e-6)
+    assert (a[:, 3] == 6).all() and (rgba[:, 3] == 255).all()
+    assert np.array_equal(a, full) or np.count_nonzero((a != full).any(axis=1)) < 0.6 * a.shape[0]
     n = C.c_uint32(0)
     assert pkg._ffi.rtb().rtb_group_size(grp._h, C.byref(n)) == 0 and n.value == 2
     with pytest.raises(pkg.RtbError) as e:

@@ -299,3 +299,53 @@ def test_scene_desc_validation_runs_before_any_device_work(pkg):
     assert ffi.rtb().rtb_scene_create(C.byref(d), 0, C.byref(h)) == ffi.RTB_ERR_INVALID_ARGUMENT
     assert ffi.rtb().rtb_scene_create(None, 0, C.byref(h)) == ffi.RTB_ERR_INVALID_ARGUMENT
     assert ffi.rtb().rtb_scene_destroy(None) == ffi.RTB_OK
+
+
+def _build_abi_smoke(pkg, tmp_path):
+    """include/rtb.h must be usable from plain C99 (no C++ / ctypes in between): compile tests/abi_smoke.c strictly."""
+    exe = str(tmp_path / "abi_smoke")
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "abi_smoke.c"), "-L", pkg._ffi.LIB_DIR, "-lrtb", f"-Wl,-rpath,{pkg._ffi.LIB_DIR}",
+           "-lm", "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_header_is_c99_clean_and_links(pkg, tmp_path):
+    exe = _build_abi_smoke(pkg, tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    n = C.c_int(0)
+    if pkg._ffi.rtb().rtb_device_count(C.byref(n)) == pkg.RTB_OK:
+        assert out.returncode == 0 and "abi_smoke ok" in out.stdout, out.stdout + out.stderr
+    else:   # no device here: the C program must see the loud RTB_ERR_NO_DEVICE, not a crash or a silent fallback
+        assert out.returncode == 77 and "no CPU fallback" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_abi_smoke_runs_from_c(pkg, tmp_path):
+    exe = _build_abi_smoke(pkg, tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "abi_smoke ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_zig_shim_declares_every_entry_point_of_the_header(pkg):
+    """integration/rtb.zig ships as source (no Zig toolchain here): at least keep it in step with include/rtb.h —
+    every function a Zig host needs is declared `pub extern fn` with the header's name, and the struct fields appear in
+    the header's order."""
+    zig = open(os.path.join(ROOT, "integration", "rtb.zig")).read()
+    declared = set(re.findall(r"pub extern fn (rtb_\w+)\(", zig))
+    test_only = {"rtb_debug_build_layout", "rtb_debug_packed_layout", "rtb_philox_device_selftest", "rtb_measure_fp32_peak"}
+    assert declared == set(pkg._ffi.RTB_SYMBOLS) - test_only
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rtb.h")).read(), flags=re.S)
+    for name in ("RtbHittable", "RtbMaterial", "RtbTexture", "RtbBvhNode", "RtbSceneDesc", "RtbCamera", "RtbRenderOptions",
+                 "RtbRenderStats"):
+        body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", header, flags=re.S).group(1)
+        c_fields = [re.sub(r"\[.*", "", f.strip().split()[-1]).lstrip("*") for f in body.split(";") if f.strip()]
+        z_body = re.search(r"pub const " + name + r" = extern struct \{(.*?)\n\};", zig, flags=re.S).group(1)
+        z_fields = re.findall(r"^\s*(\w+):", z_body, flags=re.M)
+        assert z_fields == c_fields, (name, z_fields, c_fields)
+    lower = open(os.path.join(ROOT, "integration", "lower.zig")).read()
+    for fn in ("lowerTexture", "lowerMaterial", "lowerHittable", "lowerNode", "lowerImages", "lowerWorld", "lowerCamera",
+               "startRender", "stopRender", "shouldStopRender", "renderOnAllGpus"):
+        assert re.search(r"pub fn " + fn + r"\(", lower), fn

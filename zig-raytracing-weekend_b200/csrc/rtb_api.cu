@@ -821,6 +821,7 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     sc->dev.oct_n_nodes[2] = n_tree_sah;
     sc->dev.n_objects = desc->n_hittables;
     sc->dev.has_quads = quads.empty() ? 0u : 1u;
+    sc->dev.n_perlins = desc->n_perlins;
     sc->nodes_fit_smem = sc->dev.n_nodes > 0 && (size_t)sc->dev.n_nodes * 32u <= megakernel_max_smem_nodes_bytes();
     *scene_out = sc;
     return RTB_OK;

@@ -96,6 +96,7 @@ struct DevScene {
     const DevImage* images;
     const DevQuad* quads;
     uint32_t has_quads;
+    uint32_t n_perlins;
 };
 
 struct DevCamera {
@@ -536,22 +537,25 @@ __device__ __forceinline__ void packed_axis_pack(float inv, float nod, float mag
     I = h2_bits(__float2half_rn(sigma * (inv * (1.0f - k))), __float2half_rn(sigma * -(inv * (1.0f + k))));
     N = h2_bits(__float2half_rn(sigma * (nod * (1.0f - k) - E)), __float2half_rn(sigma * (-(nod * (1.0f + k)) - E)));
 }
-__device__ __forceinline__ PackedRay packed_ray_setup(const DevScene& sc, float3 o, float3 d) {
-    PackedRay pr;
-    float ix, iy, iz, nx, ny, nz, mx, my, mz;
-    packed_axis_terms(o.x, d.x, sc.pk_center[0], sc.pk_inv_scale[0], sc.pk_scale[0], ix, nx, mx);
-    packed_axis_terms(o.y, d.y, sc.pk_center[1], sc.pk_inv_scale[1], sc.pk_scale[1], iy, ny, my);
-    packed_axis_terms(o.z, d.z, sc.pk_center[2], sc.pk_inv_scale[2], sc.pk_scale[2], iz, nz, mz);
-    // binary16 holds |x| < 65504: a ray far from the scene (|o_n| large: a bounce off the ground sphere thousands of
-    // units away) or nearly parallel to an axis has |inv| + |nod| beyond that.  Rounding errors are relative, so the
-    // whole ray is simply scaled by a power of two: t' = sigma * t, with the interval (t_min, t_max) scaled alike.
+// binary16 holds |x| < 65504: a ray far from the scene (|o_n| large: a bounce off the ground sphere thousands of units
+// away) or nearly parallel to an axis has |inv| + |nod| beyond that.  Rounding errors are relative, so the whole ray is
+// simply scaled by a power of two: t' = sigma * t, with the interval (t_min, t_max) scaled alike.
+__device__ __forceinline__ float packed_sigma(float mx, float my, float mz) {
     float m = 0.0f;
     if (mx < 3.0e38f) m = fmaxf(m, mx);
     if (my < 3.0e38f) m = fmaxf(m, my);
     if (mz < 3.0e38f) m = fmaxf(m, mz);
     const int e = (int)(__float_as_uint(m) >> 23) - 127;                 // floor(log2 m), m >= 0 finite
     const int kk = e > 12 ? (e - 12 > 120 ? 120 : e - 12) : 0;           // keep sigma * m < 2^13
-    pr.sigma = __uint_as_float((uint32_t)(127 - kk) << 23);
+    return __uint_as_float((uint32_t)(127 - kk) << 23);
+}
+__device__ __forceinline__ PackedRay packed_ray_setup(const DevScene& sc, float3 o, float3 d) {
+    PackedRay pr;
+    float ix, iy, iz, nx, ny, nz, mx, my, mz;
+    packed_axis_terms(o.x, d.x, sc.pk_center[0], sc.pk_inv_scale[0], sc.pk_scale[0], ix, nx, mx);
+    packed_axis_terms(o.y, d.y, sc.pk_center[1], sc.pk_inv_scale[1], sc.pk_scale[1], iy, ny, my);
+    packed_axis_terms(o.z, d.z, sc.pk_center[2], sc.pk_inv_scale[2], sc.pk_scale[2], iz, nz, mz);
+    pr.sigma = packed_sigma(mx, my, mz);
     packed_axis_pack(ix, nx, mx, pr.sigma, pr.ix, pr.nx);
     packed_axis_pack(iy, ny, my, pr.sigma, pr.iy, pr.ny);
     packed_axis_pack(iz, nz, mz, pr.sigma, pr.iz, pr.nz);

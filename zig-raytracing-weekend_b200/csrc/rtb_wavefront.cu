@@ -120,6 +120,7 @@ struct WfParams {
     uint32_t segment;           // 1-based segment index of the rays in `in`
     uint32_t zero;              // always 0; only there to make an address opaque to ptxas (see traverse_octant)
     uint32_t* survivors;        // mapped host memory, [bounce] = rays entering that bounce (may be NULL)
+    uint32_t perlin_smem;       // wf_shade: number of Perlin tables to stage in shared memory (0 = read them from global)
 };
 
 __device__ __forceinline__ bool slot_pixel(const RenderParams& R, uint32_t r, uint32_t& pixel) {
@@ -312,6 +313,270 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// wf_extend_stream — the extend kernel for INCOHERENT rays (bounces >= 1) over the packed SAH16 layout.
+//
+// ncu on the plain kernel (profiles/r2d_*): bounce rays keep 14 of 32 lanes busy.  The compiler turns its node loop
+// into "walk to the next leaf, reconverge, test the leaf", and a warp pays the LONGEST leaf-to-leaf walk of its 32
+// rays every time (~100 node iterations per warp for rays that need 24 each), then idles until its longest ray is done.
+// A SIMT cost model on real Book-1 bounce rays (tools/simt_model.cpp) said two things have to change together:
+//   * lanes must not wait at a leaf: a lane PARKS the leaf (up to kParked of them) and keeps walking with the old
+//     t_max — the walk visits a superset, leaves are still tested in walk order, so the result is the same bits — and
+//     the warp tests parked leaves together when some lane's parking is full (or too few lanes can still walk);
+//   * a lane whose ray is done takes the next ray at once.  Earlier refill schemes lost to their own overhead
+//      because the per-ray prologue (loads, packed_ray_setup) and epilogue (class lookup, queue
+//     reservation) then ran with a handful of lanes; here both stay at FULL occupancy: a warp prepares 32 rays at a
+//     time into a shared-memory staging area (all lanes take part, busy or not) and buffers finished rays there too,
+//     flushing 32 results at a time.  Taking a ray = four LDS.128, retiring one = one STS.128.
+// One CTA = 16 warps sharing one staged octant layout; warps claim 32-ray groups of the CTA's chunk range from a
+// shared-memory counter.
+#ifndef RTB_STREAM_MIN_WALKERS
+#define RTB_STREAM_MIN_WALKERS 24
+#endif
+constexpr uint32_t kParked = 2;                                   // leaves a lane may park before it has to wait
+constexpr uint32_t kStreamStageBytes = 32u * 64u;                 // per warp: 32 prepared rays x 4 quads (SoA by quad)
+constexpr uint32_t kStreamResultBytes = 32u * 16u;                // per warp: 32 finished rays
+constexpr uint32_t kStreamWarpBytes = kStreamStageBytes + kStreamResultBytes;
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Prepares rays [g, g + n) of octant bin `oct` (n <= 32) into the warp's staging area: quad q of ray j at
+// stage + (q * 32 + j) * 16 = {o.xyz, time} {d.xyz, slot} {ix, iy, iz, nx} {ny, nz, sigma, queue position}.
+// (Arguments by value: a reference to the kernel's parameter block would force a copy of it into local memory.)
+struct PackedFrame {
+    float center[3], inv_scale[3], scale[3];
+};
+static __device__ __noinline__ void stream_stage_fill(const float4* __restrict__ rays, PackedFrame fr, uint32_t stage,
+                                                      uint32_t first, uint32_t n) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (lane < n) {
+        const size_t at = (size_t)first + lane;
+        const float4 a = rays[2u * at];
+        const float4 b = rays[2u * at + 1u];
+        float ix, iy, iz, nx, ny, nz, mx, my, mz;
+        packed_axis_terms(a.x, b.x, fr.center[0], fr.inv_scale[0], fr.scale[0], ix, nx, mx);
+        packed_axis_terms(a.y, b.y, fr.center[1], fr.inv_scale[1], fr.scale[1], iy, ny, my);
+        packed_axis_terms(a.z, b.z, fr.center[2], fr.inv_scale[2], fr.scale[2], iz, nz, mz);
+        const float sigma = packed_sigma(mx, my, mz);
+        uint32_t pix, piy, piz, pnx, pny, pnz;
+        packed_axis_pack(ix, nx, mx, sigma, pix, pnx);
+        packed_axis_pack(iy, ny, my, sigma, piy, pny);
+        packed_axis_pack(iz, nz, mz, sigma, piz, pnz);
+        sts128(stage + (0u * 32u + lane) * 16u, make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w)));
+        sts128(stage + (1u * 32u + lane) * 16u, make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
+        sts128(stage + (2u * 32u + lane) * 16u, make_uint4(pix, piy, piz, pnx));
+        sts128(stage + (3u * 32u + lane) * 16u, make_uint4(pny, pnz, __float_as_uint(sigma), (uint32_t)at));
+    }
+    __syncwarp();
+}
+
+// Pushes the warp's n buffered results {queue position, bits(t), object, slot} to the hit queues of their classes.
+static __device__ __noinline__ void stream_flush(uint32_t* hit_count, uint4* __restrict__ hitq, uint32_t capacity,
+                                                 const uint8_t* __restrict__ object_class, uint32_t results, uint32_t n) {
+    __syncwarp();
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool valid = lane < n;
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t cls = CLASS_MISS;
+    if (valid) {
+        e = lds128(results + lane * 16u);
+        if (e.z != 0xffffffffu) cls = object_class[e.z];
+    }
+    const uint32_t j = queue_reserve(hit_count, valid, cls);
+    if (valid) hitq[(size_t)cls * capacity + j] = e;
+    __syncwarp();
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_extend_stream(const WfParams P) {
+    __shared__ ChunkMap map;
+    __shared__ uint32_t seg_next;
+    chunk_map_init(map, P.count_in, kOctants, kExtendThreads);
+    if (blockIdx.x == 0 && threadIdx.x < kBins) {
+        P.count_out[threadIdx.x] = 0u;
+        P.hit_count_next[threadIdx.x] = 0u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.survivors && P.segment <= kSurvivorSlots) {
+        uint32_t total = 0;
+        for (uint32_t b = 0; b < kOctants; ++b) total += map.count[b];
+        P.survivors[P.segment - 1u] = total;
+    }
+    const uint32_t total_chunks = map.first_chunk[kBins];
+    const uint32_t pk_slots = P.R.scene.pk_slots;
+    const uint4* __restrict__ layouts = P.R.scene.pk_nodes;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(rtb_smem_nodes) + P.zero;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t stage = smem_base + pk_slots * 16u + warp * kStreamWarpBytes;
+    const uint32_t results = stage + kStreamStageBytes;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    constexpr uint32_t kNone = 0xffffffffu;
+    // lane state machine in one register: 0..kParked-1 = walking with that many leaves parked, kParked = parking full
+    // (waiting for a leaf phase), + kDone once the walk has reached the end sentinel, kIdle = no ray
+    constexpr uint32_t kDone = 4u, kIdle = 8u;
+    static_assert(kParked < kDone, "state encoding");
+    PackedFrame fr;
+    for (int k = 0; k < 3; ++k) {
+        fr.center[k] = P.R.scene.pk_center[k];
+        fr.inv_scale[k] = P.R.scene.pk_inv_scale[k];
+        fr.scale[k] = P.R.scene.pk_scale[k];
+    }
+    uint32_t staged = kOctants;
+    uint32_t n_box = 0, n_obj = 0, n_rays = 0;
+
+    const uint32_t per_cta = (total_chunks + gridDim.x - 1u) / gridDim.x;
+    uint32_t c = blockIdx.x * per_cta;
+    const uint32_t c_end = (blockIdx.x + 1u) * per_cta < total_chunks ? (blockIdx.x + 1u) * per_cta : total_chunks;
+    while (c < c_end) {  // one iteration per octant this CTA's chunk range touches (block-uniform)
+        uint32_t oct = 0;
+        while (c >= map.first_chunk[oct + 1u]) ++oct;
+        const uint32_t c_hi = c_end < map.first_chunk[oct + 1u] ? c_end : map.first_chunk[oct + 1u];
+        const uint32_t r0 = (c - map.first_chunk[oct]) * kExtendThreads;
+        uint32_t r1 = (c_hi - map.first_chunk[oct]) * kExtendThreads;
+        if (r1 > map.count[oct]) r1 = map.count[oct];
+        c = c_hi;
+        __syncthreads();  // every warp has left the previous segment
+        if (oct != staged) {
+            const uint4* __restrict__ src = layouts + (size_t)oct * pk_slots;
+            for (uint32_t k = threadIdx.x; k < pk_slots; k += blockDim.x) {
+                uint4 v = src[k];
+                if (v.w < (1u << 30)) v.w = smem_base + v.w * 16u;  // skip links become shared-window addresses
+                sts128(smem_base + k * 16u, v);
+            }
+            staged = oct;
+        }
+        if (threadIdx.x == 0) seg_next = r0;
+        __syncthreads();
+
+        // ---- per-warp stream over the segment's rays ----
+        uint32_t wstate = kIdle;
+        float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, time = 0.f, sigma = 1.f;
+        uint32_t slot = 0u, at = 0u, pix = 0u, piy = 0u, piz = 0u, pnx = 0u, pny = 0u, pnz = 0u;
+        uint32_t i = smem_base, pend0 = 0u, pend1 = 0u, best_obj = kNone;
+        float best_t = __int_as_float(0x7f800000);
+        __half2 K = packed_interval(0.001f, best_t, 1.0f);
+        uint32_t n_staged = 0u, taken = 0u, rcount = 0u;  // warp-uniform
+        bool exhausted = false;
+        const uint32_t bin_base = oct * P.capacity;
+        for (;;) {
+            // -- hand staged rays to idle lanes (refilling the staging area first when it is empty) --
+            const uint32_t idle = __ballot_sync(0xffffffffu, wstate == kIdle);
+            if (idle != 0u) {
+                if (taken == n_staged && !exhausted) {
+                    uint32_t g = 0u;
+                    if (lane == 0u) g = atomicAdd(&seg_next, 32u);
+                    g = __shfl_sync(0xffffffffu, g, 0);
+                    taken = 0u;
+                    if (g >= r1) {
+                        exhausted = true;
+                        n_staged = 0u;
+                    } else {
+                        n_staged = r1 - g < 32u ? r1 - g : 32u;
+                        stream_stage_fill(P.in.rays, fr, stage, bin_base + g, n_staged);
+                    }
+                }
+                const uint32_t avail = n_staged - taken;
+                if (avail != 0u) {
+                    const uint32_t rank = __popc(idle & lt_mask);
+                    if (wstate == kIdle && rank < avail) {
+                        const uint32_t rec = stage + (taken + rank) * 16u;
+                        const uint4 q0 = lds128(rec), q1 = lds128(rec + 512u), q2 = lds128(rec + 1024u), q3 = lds128(rec + 1536u);
+                        ox = __uint_as_float(q0.x); oy = __uint_as_float(q0.y); oz = __uint_as_float(q0.z); time = __uint_as_float(q0.w);
+                        dx = __uint_as_float(q1.x); dy = __uint_as_float(q1.y); dz = __uint_as_float(q1.z); slot = q1.w;
+                        pix = q2.x; piy = q2.y; piz = q2.z; pnx = q2.w;
+                        pny = q3.x; pnz = q3.y; sigma = __uint_as_float(q3.z); at = q3.w;
+                        wstate = 0u;
+                        i = smem_base;
+                        best_t = __int_as_float(0x7f800000);
+                        best_obj = kNone;
+                        K = packed_interval(0.001f, best_t, sigma);
+                        if (COUNT) ++n_rays;
+                    }
+                    const uint32_t n_idle = __popc(idle);
+                    taken += n_idle < avail ? n_idle : avail;
+                }
+            }
+            const uint32_t n_active = 32u - __popc(__ballot_sync(0xffffffffu, wstate == kIdle));
+            if (n_active == 0u) break;  // nothing staged, nothing in flight: the segment is done
+            // -- walk: every lane that can, two nodes per vote; stop when too few lanes can still walk (the others
+            //    are waiting for a leaf phase or for a new ray).  While rays can still be handed out all 32 lanes are
+            //    active and the bar is RTB_STREAM_MIN_WALKERS; when the segment drains it follows the lanes left. --
+            uint32_t min_walkers = (n_active * 3u) / 4u;
+            if (min_walkers > (uint32_t)RTB_STREAM_MIN_WALKERS) min_walkers = (uint32_t)RTB_STREAM_MIN_WALKERS;
+            if (min_walkers == 0u) min_walkers = 1u;
+            for (;;) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (wstate < kParked) {
+                        const uint4 n = lds128(i);
+                        if (n.w < (1u << 30)) {
+                            if (COUNT) ++n_box;
+                            const __half2 tx = __hfma2(as_h2(n.x), as_h2(pix), as_h2(pnx));
+                            const __half2 ty = __hfma2(as_h2(n.y), as_h2(piy), as_h2(pny));
+                            const __half2 tz = __hfma2(as_h2(n.z), as_h2(piz), as_h2(pnz));
+                            const __half2 r = __hmax2(__hmax2(tx, ty), __hmax2(tz, K));
+                            const bool miss = __hge(__high2half(r), __hneg(__low2half(r)));
+                            i = miss ? n.w : i + 16u;
+                        } else if (n.w == RTB_META_END) {
+                            wstate += kDone;
+                        } else {  // a leaf: park it, keep walking
+                            if (wstate == 0u) pend0 = i; else pend1 = i;
+                            ++wstate;
+                            i += 32u;
+                        }
+                    }
+                }
+                const uint32_t walkers = __ballot_sync(0xffffffffu, wstate < kParked);
+                if ((uint32_t)__popc(walkers) < min_walkers) break;
+            }
+            // -- test the oldest parked leaf of every lane that has one (walk order is kept: first in, first tested) --
+            if ((wstate & 3u) != 0u && wstate != kIdle) {
+                if (COUNT) ++n_obj;
+                const uint4 n = lds128(pend0), m = lds128(pend0 + 16u);
+                const float3 o = f3(ox, oy, oz), d = f3(dx, dy, dz);
+                const float3 c1 = f3(__uint_as_float(n.x), __uint_as_float(n.y), __uint_as_float(n.z));
+                const float3 cv = f3(__uint_as_float(m.x), __uint_as_float(m.y), __uint_as_float(m.z));
+                const float3 center = ((n.w >> 30) == KIND_MOVING_SPHERE) ? c1 + splat3(time) * cv : c1;
+                float root;
+                if (sphere_root_a(o, d, length_squared(d), center, __uint_as_float(m.w), 0.001f, best_t, root)) {
+                    best_t = root;
+                    best_obj = n.w & RTB_META_INDEX_MASK;
+                    K = packed_interval(0.001f, root, sigma);
+                }
+                pend0 = pend1;
+                --wstate;
+            }
+            // -- retire finished rays into the warp's result buffer (flushed 32 at a time, at full occupancy) --
+            const bool fin = wstate == kDone;
+            const uint32_t finm = __ballot_sync(0xffffffffu, fin);
+            if (finm != 0u) {
+                const uint32_t nf = __popc(finm);
+                if (rcount + nf > 32u) {
+                    stream_flush(P.hit_count, P.hitq, P.capacity, P.R.scene.object_class, results, rcount);
+                    rcount = 0u;
+                }
+                if (fin) {
+                    sts128(results + (rcount + __popc(finm & lt_mask)) * 16u, make_uint4(at, __float_as_uint(best_t), best_obj, slot));
+                    wstate = kIdle;
+                }
+                rcount += nf;
+            }
+        }
+        stream_flush(P.hit_count, P.hitq, P.capacity, P.R.scene.object_class, results, rcount);
+    }
+    if (COUNT) {
+        warp_add(&P.R.counters[0], n_rays);
+        warp_add(&P.R.counters[1], n_box);
+        warp_add(&P.R.counters[2], n_obj);
+    }
+}
+
 // One thread per hit record; every 256-record chunk belongs to one shading class.
 template <bool COUNT, bool QUADS>
 __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfParams P) {
@@ -319,9 +584,23 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
     chunk_map_init(map, P.hit_count, kShadeClasses);
     const uint32_t total_chunks = map.first_chunk[kBins];
     uint32_t n_hits = 0;
+    // Perlin tables (src/perlin.zig:76-81: 256 gradients + 3 x 256 permutation entries per NoiseTexture, 4 864 B packed)
+    // are gathered 7 x 8 x 4 times per noise-textured hit with data-dependent indices: a CTA that meets a chunk of
+    // textured hits (CLASS_OTHER) stages them in shared memory once (north_star: "perlin tables in constant or shared
+    // memory"; __constant__ would serialise the divergent indices).
+    DevScene scene = P.R.scene;
+    bool perlin_staged = false;
     for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
         uint32_t cls = 0;
         while (c >= map.first_chunk[cls + 1u]) ++cls;
+        if (P.perlin_smem != 0u && cls == CLASS_OTHER && !perlin_staged) {  // block-uniform
+            const uint32_t n16 = P.perlin_smem * (uint32_t)(sizeof(DevPerlin) / 16u);
+            const float4* __restrict__ src = reinterpret_cast<const float4*>(P.R.scene.perlins);
+            for (uint32_t k = threadIdx.x; k < n16; k += blockDim.x) rtb_smem_nodes[k] = src[k];
+            __syncthreads();
+            scene.perlins = reinterpret_cast<const DevPerlin*>(rtb_smem_nodes);
+            perlin_staged = true;
+        }
         const uint32_t i = (c - map.first_chunk[cls]) * kChunk + threadIdx.x;
         bool push = false;
         DRay next;
@@ -351,7 +630,7 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
                 key.seed = P.R.seed;
                 key.pixel = __float_as_uint(tl1.z);
                 key.sample = __float_as_uint(tl1.w);
-                const ShadeResult sr = shade_rec<QUADS>(P.R.scene, f0, f1, m0, m1, r, __uint_as_float(e.y), key, P.segment);
+                const ShadeResult sr = shade_rec<QUADS>(scene, f0, f1, m0, m1, r, __uint_as_float(e.y), key, P.segment);
                 L = L + T * sr.emitted;
                 if (sr.scatters && P.segment < P.R.cam.max_depth) {
                     T = T * sr.attenuation;
@@ -547,8 +826,27 @@ static cudaError_t wf_launch_extend_slab(const WfParams& P, bool smem_nodes, uin
     }
     return cudaGetLastError();
 }
+// RTB_EXTEND_STREAM: 0 = never use wf_extend_stream (default: measured slower, see its header and DESIGN.md section 5),
+// 1 = for bounces >= 1, 2 = for every bounce.
+static int wf_stream_mode() {
+    static const int v = [] { const char* s = std::getenv("RTB_EXTEND_STREAM"); return s && s[0] ? std::atoi(s) : 0; }();
+    return v;
+}
+template <bool COUNT>
+static cudaError_t wf_launch_extend_stream(const WfParams& P, uint32_t grid, cudaStream_t stream) {
+    const size_t smem = (size_t)P.R.scene.pk_slots * 16u + (kExtendThreads / 32u) * kStreamWarpBytes;
+    auto k = wf_extend_stream<COUNT>;
+    if (smem > 40u * 1024u) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, kExtendThreads, smem, stream>>>(P);
+    return cudaGetLastError();
+}
 template <bool COUNT, bool QUADS>
 static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
+    if (P.R.ordered == 3u && smem_nodes && !QUADS && wf_stream_mode() >= (P.segment == 1u ? 2 : 1))
+        return wf_launch_extend_stream<COUNT>(P, grid, stream);
     if (P.R.ordered == 3u) return wf_launch_extend_slab<COUNT, QUADS, kSlabPacked>(P, smem_nodes, grid, stream);
     return P.R.ordered == 2u ? wf_launch_extend_slab<COUNT, QUADS, kSlabFma>(P, smem_nodes, grid, stream)
                              : wf_launch_extend_slab<COUNT, QUADS, kSlabExact>(P, smem_nodes, grid, stream);
@@ -635,6 +933,11 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     const bool smem_nodes = p.scene.n_nodes > 0 && wf_layout_bytes(p.scene, p.ordered) <= megakernel_max_smem_nodes_bytes();
     const bool quads = p.scene.has_quads != 0u;
     const uint32_t max_grid = (uint32_t)st->sm_count * 8u;
+    // Perlin tables staged by wf_shade: up to 8 NoiseTextures (38 KB of dynamic shared memory, below the 48 KB that
+    // needs no opt-in); RTB_PERLIN_SMEM=0 reads them from global memory instead (A/B measurements).
+    static const bool perlin_smem_on = [] { const char* s = std::getenv("RTB_PERLIN_SMEM"); return !(s && s[0] == '0'); }();
+    const uint32_t perlin_count = (perlin_smem_on && p.scene.n_perlins > 0u && p.scene.n_perlins <= 8u) ? p.scene.n_perlins : 0u;
+    const size_t perlin_bytes = (size_t)perlin_count * sizeof(DevPerlin);
 
     // fork: the lanes start after everything already queued on the caller's stream
     e = cudaEventRecord(st->begin, stream);
@@ -663,6 +966,7 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         P.slots_per_sample = slots_per_sample;
         P.batch_begin = p.sample_begin + s0;
         P.batch_samples = nb;
+        P.perlin_smem = perlin_count;
         e = cudaMemsetAsync(ln.counts, 0, 4 * kBins * sizeof(uint32_t), ln.stream);
         if (e != cudaSuccess) return e;
         int cur = 0;
@@ -719,7 +1023,7 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     do {                                                                  \
         e = wf_launch_extend<C, Q>(P, smem_nodes, grid_e, ln.stream);     \
         if (e == cudaSuccess) {                                           \
-            wf_shade<C, Q><<<grid_s, 256, 0, ln.stream>>>(P);             \
+            wf_shade<C, Q><<<grid_s, 256, perlin_bytes, ln.stream>>>(P);  \
             e = cudaGetLastError();                                       \
         }                                                                 \
     } while (0)
