@@ -217,7 +217,10 @@ enum {
      * binned surface-area-heuristic tree instead of walking the host's random-axis median-split tree
      * (src/bvh.zig:48-67), and visits the near child first.  Slab test, primitive test and every hit
      * value are computed by the same code; only the set of visited nodes changes, so the same caveat
-     * as ORDERED applies.  Not used by the hit-query parity harness unless asked for. */
+     * as ORDERED applies.  Not used by the hit-query parity harness unless asked for.
+     * Its slab test is one f32 FMA per plane on boxes padded by 2^-21 of the scene extent; that margin is derived for
+     * ray origins within ~3.5x the scene extent of the origin.  For cameras much farther away use RTB_TRAVERSAL_SAH16,
+     * whose margin is computed per ray and grows with the origin's distance. */
     RTB_TRAVERSAL_SAH = 2,
     /* The SAH tree above, packed for the shared-memory walk of the wavefront integrator: a box node is ONE 16-byte
      * slot — its six planes as binary16 pairs in the tree's own normalised frame, rounded outwards — and the slab test
@@ -321,7 +324,15 @@ int rtb_render(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions*
 /* Same, with DEVICE buffers on the scene's device and the caller's CUDA stream (cudaStream_t as
  * void*; NULL = default stream).  Asynchronous with respect to the host unless `stats` is
  * non-NULL (then it synchronises the stream to read the timers/counters).  Used by the
- * multi-GPU driver so that the per-rank accumulators can be reduced in place. */
+ * multi-GPU driver so that the per-rank accumulators can be reduced in place.
+ * Two things a caller should know about the wavefront integrator:
+ *   * the FIRST wavefront render of a (scene, depth, frame size) blocks the host once, for about one batch: it learns
+ *     from the first batch at which bounce the paths have thinned out enough for the tail kernel (later renders of
+ *     the same configuration reuse the value and do not block);
+ *   * it keeps ray / hit / path-state queues on the device, allocated on first use and kept with the scene: 624 bytes
+ *     per path in flight, 8 Mi paths per pipeline lane, 4 lanes = about 21 GB for frames that fill the batches (small
+ *     frames or few samples allocate proportionally less).  If an allocation fails it pipelines over fewer lanes (slower,
+ *     same result) and only reports RTB_ERR_OUT_OF_MEMORY when not even one lane fits. */
 int rtb_render_device(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions* options,
                       float* d_accum, void* cuda_stream, RtbRenderStats* stats);
 

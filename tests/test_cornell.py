@@ -244,3 +244,30 @@ def test_cornell_smoke_render_parity(pkg, orc, integrator):
     a, _, _ = scene.render(cam, pkg.render_options(seed=3, integrator=0))
     b, _, _ = scene.render(cam, pkg.render_options(seed=3, integrator=1))
     assert np.array_equal(a, b)      # megakernel == wavefront, media included
+
+
+@pytest.mark.gpu
+def test_far_camera_needs_the_per_ray_margin_of_sah16(pkg, orc):
+    """the FMA slab test of RTB_TRAVERSAL_SAH relies on boxes padded by 2^-21 of the scene extent, a margin
+    derived for ray origins near the scene; the thin (1e-4) slabs of axis-aligned quads are the first to drop out when
+    the camera is far away.  RTB_TRAVERSAL_SAH16 carries its margin per ray (it grows with the origin's distance), so
+    from 20 and 200 scene extents away it must still find exactly the reference's hits."""
+    world = pkg.World.create(pkg.RTW_SCENE_CORNELL_BOX)
+    scene = pkg.Scene(world)
+    rng = np.random.default_rng(12)
+    for dist in (1.0e4, 1.0e5):
+        n = 20000
+        rays = np.zeros(n, dtype=np.dtype(pkg._ffi.RAY_DTYPE))
+        target = rng.uniform(0, 555, (n, 3)).astype(np.float32)
+        origin = np.array([278.0, 278.0, -dist], np.float32) + rng.uniform(-50, 50, (n, 3)).astype(np.float32)
+        rays["origin"], rays["direction"] = origin, target - origin
+        rays["time"], rays["t_min"], rays["t_max"] = 0.0, 0.001, np.inf
+        cpu = orc.trace_rays(world.desc, rays)
+        assert (cpu["object"] >= 0).mean() > 0.9
+        got = scene.trace_rays(rays, traversal=pkg.RTB_TRAVERSAL_SAH16)
+        # coincident surfaces (box bottoms in the floor quad) may swap owner, everything else is the reference's hit
+        same = got["object"] == cpu["object"]
+        assert np.array_equal(got["t"], cpu["t"])
+        assert (~same).mean() < 0.02 and (np.abs(cpu["p"][~same][:, 1]) < 1e-2).all()
+        ref = scene.trace_rays(rays, traversal=pkg.RTB_TRAVERSAL_REFERENCE)
+        assert np.array_equal(ref["object"], cpu["object"]) and np.array_equal(ref["t"], cpu["t"])
