@@ -603,7 +603,7 @@ def run_ours(a):
     # -- BASELINE configs[4]: the 8K Book-1 frame, STRONG scaling (the ranks share the samples), same build, same run --
     c5 = None
     if want_c5:
-        c5_spp = 64
+        c5_spp = 256   # 8.5 G paths per step: enough samples per rank at N = 8 (32) for the batches to fill
         camo5 = p.book1_camera(c5_W, c5_spp, a.depth)
         cam5 = camo5.init()
         n5 = cam5.image_width * cam5.image_height
