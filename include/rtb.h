@@ -45,7 +45,21 @@ typedef enum RtbStatus {
 /* Hittable variants lowered from the tagged union at src/objects.zig:39-47.
  * LIST/TRANSLATE/ROTATE_Y/CONSTANT_MEDIUM are SURVEY §8(f) "next" rows; RoundBox is unfinished
  * in the reference (src/objects.zig:171-192) and has no tag. */
-enum { RTB_HITTABLE_SPHERE = 0, RTB_HITTABLE_QUAD = 1, RTB_HITTABLE_BOX = 2, RTB_HITTABLE_CONSTANT_MEDIUM = 3 };
+enum {
+    RTB_HITTABLE_SPHERE = 0,
+    RTB_HITTABLE_QUAD = 1,
+    RTB_HITTABLE_BOX = 2,             /* Translate(RotateY(createBox)) as ONE record (the shape HEAD's scenes build) */
+    RTB_HITTABLE_CONSTANT_MEDIUM = 3, /* ConstantMedium over such a box                                             */
+    /* General instancing (src/objects.zig:264-443): wrappers refer to OTHER entries of RtbSceneDesc.hittables through
+     * `child`; wrapped entries are not BVH leaves themselves.  child must be greater than the wrapper's own index
+     * (no cycles), list members are contiguous. */
+    RTB_HITTABLE_TRANSLATE = 4,       /* Translate{offset = a, object = hittables[child]}           (:308-346) */
+    RTB_HITTABLE_ROTATE_Y = 5,        /* RotateY{sin_theta, cos_theta, object = hittables[child]}   (:348-443) */
+    RTB_HITTABLE_LIST = 6,            /* HittableList{objects = hittables[child .. child + count)}, count in `material`
+                                       * (:264-305): members tried in order with ray_t.max = closest so far          */
+    RTB_HITTABLE_MEDIUM_OF = 7        /* ConstantMedium{boundary = hittables[child], neg_inv_density = radius,
+                                       * phase_function = material} over ANY boundary (:445-508)                      */
+};
 
 /* Material variants, src/material.zig:11-16. */
 enum {
@@ -74,19 +88,23 @@ enum { RTB_TEX_SOLID = 0, RTB_TEX_CHECKER = 1, RTB_TEX_IMAGE = 2, RTB_TEX_NOISE 
  *            (:484); that draw is word 0 of Philox block (0x40000000 + object index) of the ray
  *            segment's stream, so it does not depend on the traversal order.  For rtb_trace_rays the
  *            stream is keyed (seed 0; pixel = ray index, sample 0, segment 1).
+ *   translate / rotate_y / list / medium_of: the general wrappers, see the enum above.  The object index reported for
+ *            a hit inside a wrapper is the index of the TOP-LEVEL object (the BVH leaf); its material is the hit
+ *            primitive's.  A medium_of's random draw is keyed by the medium's own index (block 0x40000000 + index).
  * The bounding box is not carried here: the BVH nodes hold the boxes the host computed
  * (Sphere.init / initMoving, src/objects.zig:80-92; RotateY.init :360-397; Translate.init :314-319). */
 typedef struct RtbHittable {
     uint32_t type;      /* RTB_HITTABLE_* */
-    uint32_t material;  /* index into RtbSceneDesc.materials (the reference stores Material by value) */
+    uint32_t material;  /* index into RtbSceneDesc.materials (the reference stores Material by value);
+                         * list: the number of members; translate / rotate_y: unused */
     uint32_t is_moving; /* sphere only, src/objects.zig:72 */
     float radius;       /* sphere only */
     float a[3];
     float b[3];
     float c[3];
-    float sin_theta; /* box only */
-    float cos_theta; /* box only */
-    uint32_t reserved;
+    float sin_theta; /* box, rotate_y */
+    float cos_theta; /* box, rotate_y */
+    uint32_t child;  /* translate / rotate_y / medium_of: index of the wrapped hittable; list: of its first member */
 } RtbHittable; /* 64 bytes */
 
 /* src/material.zig:32-144.
@@ -302,7 +320,11 @@ const char* rtb_last_error(void);
 int rtb_device_count(int* count);
 
 /* Copies the scene to `device` (cudaSetDevice ordinal).  Replaces: nothing is copied in the
- * reference — world is read in place by the worker threads (src/camera.zig:104). */
+ * reference — world is read in place by the worker threads (src/camera.zig:104).
+ * The caller's arrays are not retained.  The device layouts of a traversal mode (eight per-octant copies of the tree)
+ * are built and uploaded on the first render / ray query that uses the mode, from a host copy of the nodes and
+ * hittables the scene keeps; that first call pays for it (tens of milliseconds on Book-1, seconds on a million
+ * objects). */
 int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene** scene_out);
 int rtb_scene_destroy(RtbScene* scene);
 

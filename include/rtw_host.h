@@ -81,6 +81,20 @@ int rtw_world_add_box(RtwWorld* world, const float a[3], const float b[3], int r
  * (src/objects.zig:450-452; cornellBoxSmoke src/main.zig:223-236). */
 int rtw_world_add_medium(RtwWorld* world, const float a[3], const float b[3], int rotate, float angle_degrees,
                          const float* offset_or_null, float density, const float color[3]);
+/* General instancing (src/objects.zig:264-443): objects are first built DETACHED — every call returns a handle —,
+ * wrapped as often as wanted in any order (the wrapper copies the wrapped object, as the reference copies `obj` into
+ * allocator.create(Hittable)), and finally attached to the world list with rtw_world_add_object. */
+int rtw_obj_sphere(RtwWorld* world, const float center1[3], const float* center2_or_null, float radius,
+                   const RtwMaterialSpec* material, uint32_t* handle_out);
+int rtw_obj_quad(RtwWorld* world, const float q[3], const float u[3], const float v[3], const RtwMaterialSpec* material,
+                 uint32_t* handle_out);
+int rtw_obj_box(RtwWorld* world, const float a[3], const float b[3], const RtwMaterialSpec* material,
+                uint32_t* handle_out);                                                  /* createBox */
+int rtw_obj_list(RtwWorld* world, const uint32_t* handles, uint32_t n, uint32_t* handle_out); /* HittableList, in order */
+int rtw_obj_translate(RtwWorld* world, uint32_t handle, const float offset[3], uint32_t* handle_out);
+int rtw_obj_rotate_y(RtwWorld* world, uint32_t handle, float angle_degrees, uint32_t* handle_out);
+int rtw_obj_medium(RtwWorld* world, uint32_t boundary, float density, const float color[3], uint32_t* handle_out);
+int rtw_world_add_object(RtwWorld* world, uint32_t handle);
 int rtw_world_build(RtwWorld* world, uint64_t bvh_seed); /* BVHTree.init + lowering */
 
 const RtbSceneDesc* rtw_world_desc(const RtwWorld* world); /* valid until rtw_world_destroy */

@@ -133,14 +133,21 @@ pub fn lowerMaterial(l: *Lowered, mat: Material) LowerError!u32 {
 /// A `createBox(a, b, mat)` list (src/objects.zig:510-532): six quads that share one material.  The two corners handed
 /// to createBox are recovered as the extrema of the quads' corners (q, q + u, q + v, q + u + v); the library rebuilds
 /// the same six quads from them, in createBox's order — including HEAD's quirk of emitting the z = min face twice and
-/// no z = max face (:520-529), which tests/test_cornell.py pins.
-fn boxCorners(list: objects.HittableList, a: *[3]f32, b: *[3]f32, mat: *Material) LowerError!void {
-    if (list.objects.items.len != 6) return LowerError.Unsupported;
+/// no z = max face (:520-529), which tests/test_cornell.py pins.  Returns false if the list is not such a box.
+fn boxCorners(list: objects.HittableList, a: *[3]f32, b: *[3]f32, mat: *Material) bool {
+    if (list.objects.items.len != 6) return false;
     var mn = [3]f32{ std.math.inf(f32), std.math.inf(f32), std.math.inf(f32) };
     var mx = [3]f32{ -std.math.inf(f32), -std.math.inf(f32), -std.math.inf(f32) };
     for (list.objects.items) |side| {
         switch (side) {
             .quad => |q| {
+                // createBox's quads are axis-aligned: u and v each have exactly one non-zero component
+                var nz: u32 = 0;
+                for (0..3) |k| {
+                    if (q.u[k] != 0) nz += 1;
+                    if (q.v[k] != 0) nz += 1;
+                }
+                if (nz != 2) return false;
                 const corners = [4]Vec3{ q.q, q.q + q.u, q.q + q.v, q.q + q.u + q.v };
                 for (corners) |c| {
                     for (0..3) |k| {
@@ -150,16 +157,18 @@ fn boxCorners(list: objects.HittableList, a: *[3]f32, b: *[3]f32, mat: *Material
                 }
                 mat.* = q.mat;
             },
-            else => return LowerError.Unsupported,
+            else => return false,
         }
     }
     a.* = mn;
     b.* = mx;
+    return true;
 }
 
-/// The instancing shapes HEAD's scenes use (src/main.zig:182-190, :223-236): a createBox list, optionally wrapped in
-/// RotateY and / or Translate.  Fills the box fields of `out`; returns the box's material.
-fn lowerBoxInstance(h: Hittable, out: *rtb.RtbHittable) LowerError!Material {
+/// The fast path for the instancing shape HEAD's scenes use (src/main.zig:182-190, :223-236): a createBox list,
+/// optionally wrapped in RotateY and / or Translate (in that nesting), becomes ONE RtbHittable of type BOX.
+/// Returns null when `h` is anything else — the caller then lowers it with the general wrappers.
+fn lowerBoxInstance(h: Hittable, out: *rtb.RtbHittable) ?Material {
     var cur = h;
     out.c = .{ 0, 0, 0 };
     out.sin_theta = 0;
@@ -173,15 +182,16 @@ fn lowerBoxInstance(h: Hittable, out: *rtb.RtbHittable) LowerError!Material {
         out.cos_theta = cur.rotate_y.cos_theta;
         cur = cur.rotate_y.object.*;
     }
-    if (cur != .list) return LowerError.Unsupported; // a Translate / RotateY of something other than createBox
+    if (cur != .list) return null;
     var mat: Material = undefined;
-    try boxCorners(cur.list, &out.a, &out.b, &mat);
+    if (!boxCorners(cur.list, &out.a, &out.b, &mat)) return null;
     return mat;
 }
 
-/// One `world_objects.items[i]` (src/objects.zig:39-47) -> RtbHittable at the SAME index i: the position in the
-/// object list is the "object index" rtb_trace_rays reports, and BVH leaves refer to it.
-pub fn lowerHittable(l: *Lowered, h: Hittable) LowerError!void {
+/// Any Hittable (src/objects.zig:39-47) -> l.hittables[at].  Wrappers (Translate / RotateY / HittableList /
+/// ConstantMedium over anything) refer to their wrapped objects through `child`; those are appended AFTER everything
+/// already in the array (a child always follows its wrapper, list members are contiguous), recursively.
+pub fn lowerInto(l: *Lowered, at: usize, h: Hittable) LowerError!void {
     var out = rtb.RtbHittable{ .type = rtb.HITTABLE_SPHERE, .material = 0 };
     switch (h) {
         .sphere => |s| {
@@ -200,20 +210,58 @@ pub fn lowerHittable(l: *Lowered, h: Hittable) LowerError!void {
             out.material = try lowerMaterial(l, q.mat);
         },
         .list, .translate, .rotate_y => {
-            out.type = rtb.HITTABLE_BOX;
-            const mat = try lowerBoxInstance(h, &out);
-            out.material = try lowerMaterial(l, mat);
+            if (lowerBoxInstance(h, &out)) |mat| { // the one-record fast path
+                out.type = rtb.HITTABLE_BOX;
+                out.material = try lowerMaterial(l, mat);
+            } else switch (h) {
+                .translate => |t| { // Translate{offset, object} (src/objects.zig:308-311)
+                    out.type = rtb.HITTABLE_TRANSLATE;
+                    out.a = v3(t.offset);
+                    out.child = @intCast(l.hittables.items.len);
+                    try l.hittables.append(undefined);
+                    try lowerInto(l, out.child, t.object.*);
+                },
+                .rotate_y => |r| { // RotateY{object, sin_theta, cos_theta} (:348-352)
+                    out.type = rtb.HITTABLE_ROTATE_Y;
+                    out.sin_theta = r.sin_theta;
+                    out.cos_theta = r.cos_theta;
+                    out.child = @intCast(l.hittables.items.len);
+                    try l.hittables.append(undefined);
+                    try lowerInto(l, out.child, r.object.*);
+                },
+                .list => |ls| { // HittableList{objects} (:264-267): members contiguous, in order
+                    if (ls.objects.items.len == 0) return LowerError.Unsupported;
+                    out.type = rtb.HITTABLE_LIST;
+                    out.material = @intCast(ls.objects.items.len); // a list has no material: the field carries the count
+                    out.child = @intCast(l.hittables.items.len);
+                    for (ls.objects.items) |_| try l.hittables.append(undefined);
+                    for (ls.objects.items, 0..) |member, k| try lowerInto(l, out.child + k, member);
+                },
+                else => unreachable,
+            }
         },
-        .constant_medium => |m| { // src/objects.zig:445-508: boundary = a box instance, phase function = Isotropic
-            out.type = rtb.HITTABLE_CONSTANT_MEDIUM;
-            _ = try lowerBoxInstance(m.boundary.*, &out);
+        .constant_medium => |m| { // src/objects.zig:445-452
             out.radius = m.neg_inv_density; // -1 / density (:451)
             out.material = try lowerMaterial(l, m.phase_function);
+            if (lowerBoxInstance(m.boundary.*, &out)) |_| {
+                out.type = rtb.HITTABLE_CONSTANT_MEDIUM; // fog in a box instance: one record (cornellBoxSmoke)
+            } else {
+                out.type = rtb.HITTABLE_MEDIUM_OF; // fog inside any other boundary
+                out.child = @intCast(l.hittables.items.len);
+                try l.hittables.append(undefined);
+                try lowerInto(l, out.child, m.boundary.*);
+            }
         },
         .round_box => return LowerError.Unsupported, // unfinished in the reference (src/objects.zig:171-192)
         .tree => return LowerError.Unsupported, // a tree inside a tree does not occur in HEAD's scenes
     }
-    try l.hittables.append(out);
+    l.hittables.items[at] = out;
+}
+
+/// One `world_objects.items[i]` -> RtbHittable at the SAME index i: the position in the object list is the "object
+/// index" rtb_trace_rays reports, and BVH leaves refer to it.  (Children of wrappers land behind the list.)
+pub fn lowerHittable(l: *Lowered, i: usize, h: Hittable) LowerError!void {
+    try lowerInto(l, i, h);
 }
 
 /// BVHNode pointer graph (src/bvh.zig:106-110) -> index-linked RtbBvhNode array, any order (the library re-lays the
@@ -245,7 +293,8 @@ pub fn lowerImages(l: *Lowered, images: std.ArrayList(zstbi.Image)) LowerError!v
 pub fn lowerWorld(allocator: std.mem.Allocator, world: Hittable, world_objects: []const Hittable, images: std.ArrayList(zstbi.Image)) LowerError!Lowered {
     var l = Lowered.init(allocator);
     errdefer l.deinit();
-    for (world_objects) |h| try lowerHittable(&l, h); // index i of world_objects.items -> hittables[i]
+    try l.hittables.resize(world_objects.len); // index i of world_objects.items -> hittables[i]; children follow
+    for (world_objects, 0..) |h, i| try lowerHittable(&l, i, h);
     try lowerImages(&l, images);
     switch (world) {
         .tree => |t| l.root = try lowerNode(&l, t.root, world_objects.ptr),

@@ -23,6 +23,10 @@ pub const HITTABLE_SPHERE: u32 = 0;
 pub const HITTABLE_QUAD: u32 = 1;
 pub const HITTABLE_BOX: u32 = 2; // Translate(RotateY(createBox(a, b, mat), angle), offset)
 pub const HITTABLE_CONSTANT_MEDIUM: u32 = 3;
+pub const HITTABLE_TRANSLATE: u32 = 4; // general wrappers: `child` indexes another entry of the hittable array
+pub const HITTABLE_ROTATE_Y: u32 = 5;
+pub const HITTABLE_LIST: u32 = 6;
+pub const HITTABLE_MEDIUM_OF: u32 = 7;
 
 pub const MAT_LAMBERTIAN: u32 = 0;
 pub const MAT_METAL: u32 = 1;
@@ -61,7 +65,7 @@ pub const RtbHittable = extern struct { // 64 bytes
     c: [3]f32 = .{ 0, 0, 0 },
     sin_theta: f32 = 0,
     cos_theta: f32 = 1,
-    reserved: u32 = 0,
+    child: u32 = 0, // translate / rotate_y / medium_of: the wrapped hittable; list: its first member (count in `material`)
 };
 
 pub const RtbMaterial = extern struct { // 32 bytes

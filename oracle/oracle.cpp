@@ -289,18 +289,93 @@ bool mediumHit(const RtbHittable& m, uint32_t index, const Ray& r, Interval ray_
     return true;
 }
 
-bool hittableHit(const RtbSceneDesc* sc, uint32_t index, const Ray& r, Interval ray_t, HitRecord& rec) {
+bool anyHit(const RtbSceneDesc* sc, uint32_t index, const Ray& r, Interval ray_t, HitRecord& rec);
+
+// Translate.hit, objects.zig:327-345
+bool translateHit(const RtbSceneDesc* sc, const RtbHittable& t, const Ray& r, Interval ray_t, HitRecord& rec) {
+    const V3 offset = v3(t.a);
+    const Ray moved{r.origin - offset, r.direction, r.time};
+    if (!anyHit(sc, t.child, moved, ray_t, rec)) return false;
+    rec.p = rec.p + offset;
+    return true;
+}
+
+// RotateY.hit, objects.zig:404-442
+bool rotateYHit(const RtbSceneDesc* sc, const RtbHittable& ry, const Ray& r, Interval ray_t, HitRecord& rec) {
+    const float sin_theta = ry.sin_theta, cos_theta = ry.cos_theta;
+    V3 origin = r.origin, direction = r.direction;
+    origin.x = cos_theta * r.origin.x - sin_theta * r.origin.z;
+    origin.z = sin_theta * r.origin.x + cos_theta * r.origin.z;
+    direction.x = cos_theta * r.direction.x - sin_theta * r.direction.z;
+    direction.z = sin_theta * r.direction.x + cos_theta * r.direction.z;
+    const Ray rotated{origin, direction, r.time};
+    HitRecord h;
+    if (!anyHit(sc, ry.child, rotated, ray_t, h)) return false;
+    rec = h;
+    rec.p.x = cos_theta * h.p.x + sin_theta * h.p.z;
+    rec.p.z = -sin_theta * h.p.x + cos_theta * h.p.z;
+    rec.normal.x = cos_theta * h.normal.x + sin_theta * h.normal.z;
+    rec.normal.z = -sin_theta * h.normal.x + cos_theta * h.normal.z;
+    return true;
+}
+
+// HittableList.hit, objects.zig:286-304: members in order, ray_t.max = closest so far
+bool listHit(const RtbSceneDesc* sc, const RtbHittable& l, const Ray& r, Interval ray_t, HitRecord& rec) {
+    bool hit = false;
+    float closest_so_far = ray_t.max;
+    for (uint32_t k = 0; k < l.material; ++k) {  // `material` carries the member count of a list
+        HitRecord cand;
+        if (anyHit(sc, l.child + k, r, Interval{ray_t.min, closest_so_far}, cand)) {
+            closest_so_far = cand.t;
+            rec = cand;
+            hit = true;
+        }
+    }
+    return hit;
+}
+
+// ConstantMedium.hit (objects.zig:462-507) over ANY boundary hittable.
+bool mediumOfHit(const RtbSceneDesc* sc, const RtbHittable& m, uint32_t index, const Ray& r, Interval ray_t, HitRecord& rec) {
+    HitRecord rec_1, rec_2;
+    if (!anyHit(sc, m.child, r, Interval{-kInfinity, kInfinity}, rec_1)) return false;
+    if (!anyHit(sc, m.child, r, Interval{rec_1.t + 0.0001f, kInfinity}, rec_2)) return false;
+    if (rec_1.t < ray_t.min) rec_1.t = ray_t.min;
+    if (rec_2.t > ray_t.max) rec_2.t = ray_t.max;
+    if (rec_1.t >= rec_2.t) return false;
+    if (rec_1.t < 0) rec_1.t = 0;
+    const float ray_length = length(r.direction);
+    const float distance_inside_boundary = (rec_2.t - rec_1.t) * ray_length;
+    const float rnd = rng_block(g_ctx.seed, g_ctx.pixel, g_ctx.sample, g_ctx.segment, 0x40000000u + index).r[0];
+    const float hit_distance = m.radius * std::log(rnd);
+    if (hit_distance > distance_inside_boundary) return false;
+    rec = HitRecord{};
+    rec.t = rec_1.t + hit_distance / ray_length;
+    rec.p = at(r, rec.t);
+    rec.normal = v3(1, 0, 0);
+    rec.front_face = true;
+    rec.mat = m.material;
+    return true;
+}
+
+// Hittable.hit on any entry of the hittable array (top-level object or a wrapper's child).
+bool anyHit(const RtbSceneDesc* sc, uint32_t index, const Ray& r, Interval ray_t, HitRecord& rec) {
     const RtbHittable& h = sc->hittables[index];
-    bool ok = false;
-    if (h.type == RTB_HITTABLE_SPHERE)
-        ok = sphereHit(h, r, ray_t, rec);
-    else if (h.type == RTB_HITTABLE_QUAD)
-        ok = quadHit(h, r, ray_t, rec);
-    else if (h.type == RTB_HITTABLE_BOX)
-        ok = boxHit(h, r, ray_t, rec);
-    else if (h.type == RTB_HITTABLE_CONSTANT_MEDIUM)
-        ok = mediumHit(h, index, r, ray_t, rec);
-    if (ok) rec.object = (int32_t)index;
+    switch (h.type) {
+        case RTB_HITTABLE_SPHERE: return sphereHit(h, r, ray_t, rec);
+        case RTB_HITTABLE_QUAD: return quadHit(h, r, ray_t, rec);
+        case RTB_HITTABLE_BOX: return boxHit(h, r, ray_t, rec);
+        case RTB_HITTABLE_CONSTANT_MEDIUM: return mediumHit(h, index, r, ray_t, rec);
+        case RTB_HITTABLE_TRANSLATE: return translateHit(sc, h, r, ray_t, rec);
+        case RTB_HITTABLE_ROTATE_Y: return rotateYHit(sc, h, r, ray_t, rec);
+        case RTB_HITTABLE_LIST: return listHit(sc, h, r, ray_t, rec);
+        case RTB_HITTABLE_MEDIUM_OF: return mediumOfHit(sc, h, index, r, ray_t, rec);
+        default: return false;
+    }
+}
+
+bool hittableHit(const RtbSceneDesc* sc, uint32_t index, const Ray& r, Interval ray_t, HitRecord& rec) {
+    const bool ok = anyHit(sc, index, r, ray_t, rec);
+    if (ok) rec.object = (int32_t)index;  // the top-level object (the BVH leaf), whatever is nested inside it
     return ok;
 }
 

@@ -159,6 +159,38 @@ class World:
                                                float(angle or 0.0), off, float(density), C.byref(_vec3(color))),
                "rtw_world_add_medium")
 
+    # -- general instancing: detached objects, wrapped any number of times, then attached (src/objects.zig:264-443)
+    def _handle(self, fn, *args):
+        h = _ffi.u32(0)
+        _check(fn(self._h, *args, C.byref(h)), fn.__name__)
+        return h.value
+
+    def obj_sphere(self, center, radius, spec, center2=None):
+        c2 = C.byref(_vec3(center2)) if center2 is not None else None
+        return self._handle(_ffi.rtw().rtw_obj_sphere, C.byref(_vec3(center)), c2, float(radius), C.byref(spec))
+
+    def obj_quad(self, q, u, v, spec):
+        return self._handle(_ffi.rtw().rtw_obj_quad, C.byref(_vec3(q)), C.byref(_vec3(u)), C.byref(_vec3(v)), C.byref(spec))
+
+    def obj_box(self, a, b, spec):
+        return self._handle(_ffi.rtw().rtw_obj_box, C.byref(_vec3(a)), C.byref(_vec3(b)), C.byref(spec))
+
+    def obj_list(self, handles):
+        arr = (_ffi.u32 * len(handles))(*handles)
+        return self._handle(_ffi.rtw().rtw_obj_list, arr, len(handles))
+
+    def obj_translate(self, handle, offset):
+        return self._handle(_ffi.rtw().rtw_obj_translate, handle, C.byref(_vec3(offset)))
+
+    def obj_rotate_y(self, handle, angle):
+        return self._handle(_ffi.rtw().rtw_obj_rotate_y, handle, float(angle))
+
+    def obj_medium(self, boundary, density, color):
+        return self._handle(_ffi.rtw().rtw_obj_medium, boundary, float(density), C.byref(_vec3(color)))
+
+    def add_object(self, handle):
+        _check(_ffi.rtw().rtw_world_add_object(self._h, handle), "rtw_world_add_object")
+
     def build(self, bvh_seed=2):
         _check(_ffi.rtw().rtw_world_build(self._h, bvh_seed), "rtw_world_build")
         return self

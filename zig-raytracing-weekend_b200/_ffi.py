@@ -26,6 +26,7 @@ RTB_ERR_CANCELLED = -5
 RTB_ERR_UNSUPPORTED = -6
 
 RTB_HITTABLE_SPHERE, RTB_HITTABLE_QUAD, RTB_HITTABLE_BOX, RTB_HITTABLE_CONSTANT_MEDIUM = 0, 1, 2, 3
+RTB_HITTABLE_TRANSLATE, RTB_HITTABLE_ROTATE_Y, RTB_HITTABLE_LIST, RTB_HITTABLE_MEDIUM_OF = 4, 5, 6, 7
 RTB_MAT_LAMBERTIAN, RTB_MAT_METAL, RTB_MAT_DIELECTRIC, RTB_MAT_DIFFUSE_LIGHT, RTB_MAT_ISOTROPIC = range(5)
 RTB_TEX_SOLID, RTB_TEX_CHECKER, RTB_TEX_IMAGE, RTB_TEX_NOISE = range(4)
 RTB_BACKGROUND_SOLID, RTB_BACKGROUND_SKY = 0, 1
@@ -43,7 +44,7 @@ f32, u32, i32, u64, u16, u8 = C.c_float, C.c_uint32, C.c_int32, C.c_uint64, C.c_
 class RtbHittable(C.Structure):
     _fields_ = [("type", u32), ("material", u32), ("is_moving", u32), ("radius", f32),
                 ("a", f32 * 3), ("b", f32 * 3), ("c", f32 * 3), ("sin_theta", f32), ("cos_theta", f32),
-                ("reserved", u32)]
+                ("child", u32)]
 
 
 class RtbMaterial(C.Structure):
@@ -142,7 +143,8 @@ RTB_SYMBOLS = [
 RTB_PARTITION_SAMPLES, RTB_PARTITION_TILES = 0, 1
 RTW_SYMBOLS = [
     "rtw_world_create", "rtw_world_new", "rtw_world_add_image", "rtw_world_add_sphere", "rtw_world_add_quad",
-    "rtw_world_add_box", "rtw_world_add_medium",
+    "rtw_world_add_box", "rtw_world_add_medium", "rtw_obj_sphere", "rtw_obj_quad", "rtw_obj_box", "rtw_obj_list",
+    "rtw_obj_translate", "rtw_obj_rotate_y", "rtw_obj_medium", "rtw_world_add_object",
     "rtw_world_build", "rtw_world_desc", "rtw_world_object_box", "rtw_world_destroy", "rtw_camera_defaults",
     "rtw_camera_init", "rtw_camera_render", "rtw_write_ppm", "rtw_write_png",
 ]
@@ -227,6 +229,15 @@ def rtw() -> C.CDLL:
                                       C.POINTER(RtwMaterialSpec)]
     lib.rtw_world_add_medium.argtypes = [vp, C.POINTER(f32 * 3), C.POINTER(f32 * 3), C.c_int, f32, C.POINTER(f32 * 3),
                                          f32, C.POINTER(f32 * 3)]
+    hp = C.POINTER(u32)
+    lib.rtw_obj_sphere.argtypes = [vp, C.POINTER(f32 * 3), C.POINTER(f32 * 3), f32, C.POINTER(RtwMaterialSpec), hp]
+    lib.rtw_obj_quad.argtypes = [vp, C.POINTER(f32 * 3), C.POINTER(f32 * 3), C.POINTER(f32 * 3), C.POINTER(RtwMaterialSpec), hp]
+    lib.rtw_obj_box.argtypes = [vp, C.POINTER(f32 * 3), C.POINTER(f32 * 3), C.POINTER(RtwMaterialSpec), hp]
+    lib.rtw_obj_list.argtypes = [vp, C.POINTER(u32), u32, hp]
+    lib.rtw_obj_translate.argtypes = [vp, u32, C.POINTER(f32 * 3), hp]
+    lib.rtw_obj_rotate_y.argtypes = [vp, u32, f32, hp]
+    lib.rtw_obj_medium.argtypes = [vp, u32, f32, C.POINTER(f32 * 3), hp]
+    lib.rtw_world_add_object.argtypes = [vp, u32]
     lib.rtw_world_build.argtypes = [vp, u64]
     lib.rtw_world_desc.argtypes = [vp]
     lib.rtw_world_desc.restype = C.POINTER(RtbSceneDesc)

@@ -62,6 +62,14 @@ struct RtbScene {
     uint64_t stage_pixels = 0;
     WavefrontState* wavefront = nullptr;
     std::mutex mutex;  // serialises renders on one scene (counters / wavefront queues are shared)
+    // The per-octant layouts are built and uploaded on the FIRST use of their traversal mode (ensure_layouts): eight
+    // octant copies per mode are ~25x the node memory if all modes are built up front (1.8 GB for the 1 M-sphere scene).
+    // What the builders need of the caller's description is kept here (the caller's arrays are not retained).
+    std::vector<RtbBvhNode> host_nodes;
+    std::vector<RtbHittable> host_hittables;
+    std::vector<uint32_t> host_size, host_quad_slot;
+    RtbSceneDesc host_desc{};
+    bool layout_ready[3] = {false, false, false};  // octant layouts of modes 0 (reference), 1 (ordered), 2 (SAH + SAH16)
 };
 
 struct RtbJob {
@@ -174,9 +182,19 @@ static int validate_desc(const RtbSceneDesc* d) {
         return fail(RTB_ERR_INVALID_ARGUMENT, "root %d out of range", d->root);
     for (uint32_t i = 0; i < d->n_hittables; ++i) {
         const RtbHittable& h = d->hittables[i];
-        if (h.type > RTB_HITTABLE_CONSTANT_MEDIUM)
+        if (h.type > RTB_HITTABLE_MEDIUM_OF)
             return fail(RTB_ERR_UNSUPPORTED, "hittable %u: unsupported type %u", i, h.type);
-        if (h.material >= d->n_materials) return fail(RTB_ERR_INVALID_ARGUMENT, "hittable %u: material out of range", i);
+        const bool wrapper = h.type == RTB_HITTABLE_TRANSLATE || h.type == RTB_HITTABLE_ROTATE_Y ||
+                             h.type == RTB_HITTABLE_LIST || h.type == RTB_HITTABLE_MEDIUM_OF;
+        const bool has_material = h.type != RTB_HITTABLE_TRANSLATE && h.type != RTB_HITTABLE_ROTATE_Y && h.type != RTB_HITTABLE_LIST;
+        if (has_material && h.material >= d->n_materials)
+            return fail(RTB_ERR_INVALID_ARGUMENT, "hittable %u: material out of range", i);
+        if (wrapper) {  // children come AFTER their wrapper (no cycles, bounded recursion), list members are contiguous
+            const uint64_t count = h.type == RTB_HITTABLE_LIST ? h.material : 1u;
+            if (count == 0 || h.child <= i || (uint64_t)h.child + count > d->n_hittables)
+                return fail(RTB_ERR_INVALID_ARGUMENT, "hittable %u: child range [%u, +%llu) invalid (children must follow their wrapper)",
+                            i, h.child, (unsigned long long)count);
+        }
     }
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         const RtbMaterial& m = d->materials[i];
@@ -252,6 +270,9 @@ static void leaf_record(const RtbSceneDesc* d, uint32_t object, const std::vecto
         const uint32_t kind = h.is_moving ? KIND_MOVING_SPHERE : KIND_SPHERE;
         *f0 = mkf4(h.a[0], h.a[1], h.a[2], bits((kind << 30) | object));
         *f1 = mkf4(h.b[0], h.b[1], h.b[2], h.radius);
+    } else if (h.type >= RTB_HITTABLE_TRANSLATE) {  // a general wrapper: the leaf test goes through hit_any(object)
+        *f0 = mkf4(0, 0, 0, bits((KIND_QUAD << 30) | object));
+        *f1 = mkf4(bits(COMPLEX_GENERIC), 0, 0, bits(object));
     } else {
         *f0 = mkf4(0, 0, 0, bits((KIND_QUAD << 30) | object));
         const uint32_t subtype = h.type == RTB_HITTABLE_BOX ? COMPLEX_BOX
@@ -657,6 +678,8 @@ static void pack_layout(const std::vector<float4>& oct8, uint32_t n_entries, Pac
     }
 }
 
+static int ensure_layouts(RtbScene* sc, uint32_t mode);
+
 static void scene_free(RtbScene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
@@ -685,44 +708,24 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     std::vector<DevQuad> quads;
     std::vector<uint32_t> quad_slot(desc->n_hittables, 0);
     for (uint32_t i = 0; i < desc->n_hittables; ++i) {
-        if (desc->hittables[i].type != RTB_HITTABLE_SPHERE) quad_slot[i] = append_complex(quads, desc->hittables[i]);
+        const uint32_t ty = desc->hittables[i].type;
+        if (ty == RTB_HITTABLE_QUAD || ty == RTB_HITTABLE_BOX || ty == RTB_HITTABLE_CONSTANT_MEDIUM)
+            quad_slot[i] = append_complex(quads, desc->hittables[i]);
     }
     const uint32_t n_tree = desc->n_nodes ? size[desc->root] : 0u;
     std::vector<float4> nodes(2 * (size_t)n_tree);
     emit_layout(desc, size, quad_slot, -1, false, nodes.data());
-    // per-octant layouts, [mode][octant][2 * (n_tree + 1)]; entry n_tree of every octant is the end sentinel
-    const size_t oct_stride = 2 * ((size_t)n_tree + 1);
-    const float4 sentinel = mkf4(0.0f, 0.0f, 0.0f, bits(RTB_META_END));
-    std::vector<float4> oct_nodes[3];
-    uint32_t n_tree_sah = 0;
-    for (int mode = 0; mode < 2; ++mode) {
-        oct_nodes[mode].assign(8 * oct_stride, sentinel);
-        for (int oct = 0; oct < 8; ++oct)
-            emit_layout(desc, size, quad_slot, oct, mode == 1, oct_nodes[mode].data() + (size_t)oct * oct_stride);
-    }
-    PackedLayout packed;
-    {  // mode 2: the library's own SAH partition of the objects the host's tree references
-        SahTree sah;
-        rc = sah_tree_build(desc, size, sah);
-        if (rc != RTB_OK) return rc;
-        n_tree_sah = sah.layout_nodes;
-        const size_t sah_stride = 2 * ((size_t)n_tree_sah + 1);
-        oct_nodes[2].assign(8 * sah_stride, sentinel);
-        for (int oct = 0; oct < 8; ++oct) sah_emit(desc, sah, quad_slot, oct, oct_nodes[2].data() + (size_t)oct * sah_stride);
-        // mode 3 (SAH16): the same layouts packed, when one octant fits in shared memory (else SAH16 renders as SAH)
-        if (n_tree_sah > 0 && ((size_t)n_tree_sah + 1) * 32u <= 2 * megakernel_max_smem_nodes_bytes()) {
-            pack_layout(oct_nodes[2], n_tree_sah, packed);
-            if ((size_t)packed.n_slots * 16u > megakernel_max_smem_nodes_bytes()) packed = PackedLayout{};
-        }
-    }
-
     RtbScene* sc = new (std::nothrow) RtbScene();
     if (!sc) return fail(RTB_ERR_OUT_OF_MEMORY, "host allocation failed");
     sc->device = device;
     sc->max_depth = depth;
 
+    auto has_material = [&](uint32_t i) {
+        const uint32_t ty = desc->hittables[i].type;
+        return ty != RTB_HITTABLE_TRANSLATE && ty != RTB_HITTABLE_ROTATE_Y && ty != RTB_HITTABLE_LIST;
+    };
     std::vector<uint32_t> obj_mat(desc->n_hittables);
-    for (uint32_t i = 0; i < desc->n_hittables; ++i) obj_mat[i] = desc->hittables[i].material;
+    for (uint32_t i = 0; i < desc->n_hittables; ++i) obj_mat[i] = has_material(i) ? desc->hittables[i].material : 0u;
 
     std::vector<float4> mats(2 * (size_t)desc->n_materials);
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
@@ -743,6 +746,8 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     std::vector<uint8_t> obj_class(desc->n_hittables);
     for (uint32_t i = 0; i < desc->n_hittables; ++i) {
         leaf_record(desc, i, quad_slot, &prims[4 * (size_t)i], &prims[4 * (size_t)i + 1]);
+        obj_class[i] = CLASS_OTHER;
+        if (!has_material(i) || desc->n_materials == 0) continue;  // a wrapper: shaded with the inner primitive's material
         const uint32_t m = desc->hittables[i].material;
         prims[4 * (size_t)i + 2] = mats[2 * (size_t)m];
         prims[4 * (size_t)i + 3] = mats[2 * (size_t)m + 1];
@@ -784,15 +789,21 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
         }
     }
     if (rc == RTB_OK) rc = upload(sc, nodes, &sc->dev.nodes);
-    if (rc == RTB_OK) rc = upload(sc, oct_nodes[0], &sc->dev.oct_nodes[0]);
-    if (rc == RTB_OK) rc = upload(sc, oct_nodes[1], &sc->dev.oct_nodes[1]);
-    if (rc == RTB_OK) rc = upload(sc, oct_nodes[2], &sc->dev.oct_nodes[2]);
-    if (rc == RTB_OK) rc = upload(sc, packed.slots, &sc->dev.pk_nodes);
-    sc->dev.pk_slots = packed.n_slots;
+    // keep what ensure_layouts needs (nodes + hittables of the description, subtree sizes, quad-table slots)
+    sc->host_nodes.assign(desc->nodes, desc->nodes + desc->n_nodes);
+    sc->host_hittables.assign(desc->hittables, desc->hittables + desc->n_hittables);
+    sc->host_size = size;
+    sc->host_quad_slot = quad_slot;
+    sc->host_desc = *desc;
+    sc->host_desc.nodes = sc->host_nodes.data();
+    sc->host_desc.hittables = sc->host_hittables.data();
+    sc->host_desc.materials = nullptr;  // not needed by the layout builders, and not retained
+    sc->host_desc.textures = nullptr;
+    sc->host_desc.perlins = nullptr;
+    sc->host_desc.images = nullptr;
     for (int a = 0; a < 3; ++a) {
-        sc->dev.pk_center[a] = packed.center[a];
-        sc->dev.pk_scale[a] = packed.scale[a];
-        sc->dev.pk_inv_scale[a] = 1.0f / packed.scale[a];
+        sc->dev.pk_center[a] = 0.0f;
+        sc->dev.pk_scale[a] = sc->dev.pk_inv_scale[a] = 1.0f;
     }
     if (rc == RTB_OK) rc = upload(sc, prims, &sc->dev.prims);
     if (rc == RTB_OK) rc = upload(sc, obj_class, &sc->dev.object_class);
@@ -801,7 +812,22 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     if (rc == RTB_OK) rc = upload(sc, texs, &sc->dev.textures);
     if (rc == RTB_OK) rc = upload(sc, perlins, &sc->dev.perlins);
     if (rc == RTB_OK) rc = upload(sc, images, &sc->dev.images);
+    std::vector<DevInst> insts(desc->n_hittables);
+    for (uint32_t i = 0; i < desc->n_hittables; ++i) {
+        const RtbHittable& h = desc->hittables[i];
+        DevInst in{};
+        in.type = h.type;
+        in.child = h.child;
+        in.count = h.type == RTB_HITTABLE_LIST ? h.material : 1u;
+        in.slot = quad_slot[i];
+        if (h.type == RTB_HITTABLE_TRANSLATE) in.p = mkf4(h.a[0], h.a[1], h.a[2], 0.0f);
+        else if (h.type == RTB_HITTABLE_ROTATE_Y) in.p = mkf4(h.sin_theta, h.cos_theta, 0.0f, 0.0f);
+        else if (h.type == RTB_HITTABLE_MEDIUM_OF) in.p = mkf4(h.radius, 0.0f, 0.0f, 0.0f);
+        else in.p = mkf4(0.0f, 0.0f, 0.0f, 0.0f);
+        insts[i] = in;
+    }
     if (rc == RTB_OK) rc = upload(sc, quads, &sc->dev.quads);
+    if (rc == RTB_OK) rc = upload(sc, insts, &sc->dev.insts);
     if (rc == RTB_OK) {
         void* c = nullptr;
         cudaError_t e = cudaMalloc(&c, 4 * sizeof(unsigned long long));
@@ -818,13 +844,91 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
     }
     sc->dev.n_nodes = (uint32_t)(nodes.size() / 2);
     sc->dev.oct_n_nodes[0] = sc->dev.oct_n_nodes[1] = sc->dev.n_nodes;
-    sc->dev.oct_n_nodes[2] = n_tree_sah;
+    sc->dev.oct_n_nodes[2] = 0u;
     sc->dev.n_objects = desc->n_hittables;
-    sc->dev.has_quads = quads.empty() ? 0u : 1u;
+    {   // hit_any recurses once per wrapper level: make sure the device stack holds the deepest chain of this scene
+        std::vector<uint32_t> depth(desc->n_hittables, 1u);
+        uint32_t deepest = 1u;
+        for (uint32_t i = desc->n_hittables; i-- > 0;) {  // children have larger indices than their wrapper
+            const RtbHittable& h = desc->hittables[i];
+            if (h.type < RTB_HITTABLE_TRANSLATE) continue;
+            const uint32_t count = h.type == RTB_HITTABLE_LIST ? h.material : 1u;
+            uint32_t d = 0u;
+            for (uint32_t k = 0; k < count; ++k) d = std::max(d, depth[h.child + k]);
+            depth[i] = d + 1u;
+            deepest = std::max(deepest, depth[i]);
+        }
+        if (deepest > 1u) {
+            size_t have = 0;
+            const size_t want = 1024u + 768u * (size_t)deepest;
+            if (cudaDeviceGetLimit(&have, cudaLimitStackSize) == cudaSuccess && have < want) {
+                const cudaError_t e = cudaDeviceSetLimit(cudaLimitStackSize, want);
+                if (e != cudaSuccess) {
+                    scene_free(sc);
+                    return cuda_fail(e, "cudaDeviceSetLimit(stack size for nested instances)");
+                }
+            }
+        }
+    }
+    sc->dev.has_quads = 0u;  // any object that is not a plain sphere selects the kernels that can test complex leaves
+    for (uint32_t i = 0; i < desc->n_hittables; ++i)
+        if (desc->hittables[i].type != RTB_HITTABLE_SPHERE) sc->dev.has_quads = 1u;
     sc->dev.n_perlins = desc->n_perlins;
     sc->nodes_fit_smem = sc->dev.n_nodes > 0 && (size_t)sc->dev.n_nodes * 32u <= megakernel_max_smem_nodes_bytes();
+    if (const char* eager = std::getenv("RTB_EAGER_LAYOUTS")) {  // measurement aid: build every mode's layouts now
+        if (eager[0] == '1')
+            for (uint32_t m = 0; m < 3 && rc == RTB_OK; ++m) rc = ensure_layouts(sc, m);
+        if (rc != RTB_OK) {
+            scene_free(sc);
+            return rc;
+        }
+    }
     *scene_out = sc;
     return RTB_OK;
+}
+
+// Builds and uploads the per-octant layouts of one traversal mode on first use (caller holds scene->mutex and has made
+// the scene's device current).  mode 3 (SAH16) shares mode 2's tree: both are built together.
+static int ensure_layouts(RtbScene* sc, uint32_t mode) {
+    const uint32_t slot = mode == 3u ? 2u : mode;
+    if (slot > 2u || sc->layout_ready[slot]) return RTB_OK;
+    const RtbSceneDesc* desc = &sc->host_desc;
+    const uint32_t n_tree = sc->dev.n_nodes;
+    const float4 sentinel = mkf4(0.0f, 0.0f, 0.0f, bits(RTB_META_END));
+    int rc = RTB_OK;
+    if (slot < 2u) {
+        const size_t oct_stride = 2 * ((size_t)n_tree + 1);
+        std::vector<float4> oct(8 * oct_stride, sentinel);
+        for (int o = 0; o < 8; ++o)
+            emit_layout(desc, sc->host_size, sc->host_quad_slot, o, slot == 1u, oct.data() + (size_t)o * oct_stride);
+        rc = upload(sc, oct, &sc->dev.oct_nodes[slot]);
+    } else {
+        SahTree sah;
+        rc = sah_tree_build(desc, sc->host_size, sah);
+        if (rc != RTB_OK) return rc;
+        const uint32_t n_sah = sah.layout_nodes;
+        const size_t sah_stride = 2 * ((size_t)n_sah + 1);
+        std::vector<float4> oct(8 * sah_stride, sentinel);
+        for (int o = 0; o < 8; ++o) sah_emit(desc, sah, sc->host_quad_slot, o, oct.data() + (size_t)o * sah_stride);
+        rc = upload(sc, oct, &sc->dev.oct_nodes[2]);
+        sc->dev.oct_n_nodes[2] = n_sah;
+        // SAH16: the same layouts packed, when one octant fits in shared memory (else SAH16 renders as SAH)
+        if (rc == RTB_OK && n_sah > 0 && ((size_t)n_sah + 1) * 32u <= 2 * megakernel_max_smem_nodes_bytes()) {
+            PackedLayout packed;
+            pack_layout(oct, n_sah, packed);
+            if ((size_t)packed.n_slots * 16u <= megakernel_max_smem_nodes_bytes()) {
+                rc = upload(sc, packed.slots, &sc->dev.pk_nodes);
+                sc->dev.pk_slots = packed.n_slots;
+                for (int a = 0; a < 3; ++a) {
+                    sc->dev.pk_center[a] = packed.center[a];
+                    sc->dev.pk_scale[a] = packed.scale[a];
+                    sc->dev.pk_inv_scale[a] = 1.0f / packed.scale[a];
+                }
+            }
+        }
+    }
+    if (rc == RTB_OK) sc->layout_ready[slot] = true;
+    return rc;
 }
 
 // Test hook: the host-side re-layout of one (mode, octant) without touching a device, so that the CPU
@@ -840,8 +944,11 @@ extern "C" int rtb_debug_build_layout(const RtbSceneDesc* desc, uint32_t mode, u
     if (rc != RTB_OK) return rc;
     std::vector<uint32_t> quad_slot(desc->n_hittables, 0);
     std::vector<DevQuad> table;
-    for (uint32_t i = 0; i < desc->n_hittables; ++i)
-        if (desc->hittables[i].type != RTB_HITTABLE_SPHERE) quad_slot[i] = append_complex(table, desc->hittables[i]);
+    for (uint32_t i = 0; i < desc->n_hittables; ++i) {
+        const uint32_t ty = desc->hittables[i].type;
+        if (ty == RTB_HITTABLE_QUAD || ty == RTB_HITTABLE_BOX || ty == RTB_HITTABLE_CONSTANT_MEDIUM)
+            quad_slot[i] = append_complex(table, desc->hittables[i]);
+    }
     const uint32_t n_host = desc->n_nodes ? size[desc->root] : 0u;
     SahTree sah;
     if (mode == RTB_TRAVERSAL_SAH) {
@@ -872,8 +979,11 @@ extern "C" int rtb_debug_packed_layout(const RtbSceneDesc* desc, uint32_t octant
     if (rc != RTB_OK) return rc;
     std::vector<uint32_t> quad_slot(desc->n_hittables, 0);
     std::vector<DevQuad> table;
-    for (uint32_t i = 0; i < desc->n_hittables; ++i)
-        if (desc->hittables[i].type != RTB_HITTABLE_SPHERE) quad_slot[i] = append_complex(table, desc->hittables[i]);
+    for (uint32_t i = 0; i < desc->n_hittables; ++i) {
+        const uint32_t ty = desc->hittables[i].type;
+        if (ty == RTB_HITTABLE_QUAD || ty == RTB_HITTABLE_BOX || ty == RTB_HITTABLE_CONSTANT_MEDIUM)
+            quad_slot[i] = append_complex(table, desc->hittables[i]);
+    }
     SahTree sah;
     rc = sah_tree_build(desc, size, sah);
     if (rc != RTB_OK) return rc;
@@ -912,9 +1022,13 @@ extern "C" int rtb_trace_rays(RtbScene* scene, const RtbRay* rays, uint64_t n, u
     if (n && (!rays || !hits_out)) return fail(RTB_ERR_INVALID_ARGUMENT, "rays/hits_out is NULL");
     if (traversal > RTB_TRAVERSAL_SAH16) return fail(RTB_ERR_UNSUPPORTED, "traversal mode %u not supported", traversal);
     if (n == 0) return RTB_OK;
-    if (traversal == RTB_TRAVERSAL_SAH16 && !scene->dev.pk_nodes) traversal = RTB_TRAVERSAL_SAH;  // too large to pack
     std::lock_guard<std::mutex> lock(scene->mutex);
     RTB_CUDA(cudaSetDevice(scene->device));
+    if (traversal != RTB_TRAVERSAL_REFERENCE) {  // ray queries in reference order walk the (min, max) layout built at creation
+        const int rc = ensure_layouts(scene, traversal);
+        if (rc != RTB_OK) return rc;
+    }
+    if (traversal == RTB_TRAVERSAL_SAH16 && !scene->dev.pk_nodes) traversal = RTB_TRAVERSAL_SAH;  // too large to pack
     RtbRay* d_rays = nullptr;
     RtbHit* d_hits = nullptr;
     RTB_CUDA(cudaMalloc(&d_rays, n * sizeof(RtbRay)));
@@ -984,6 +1098,11 @@ static uint64_t owned_pixels(const RtbCamera* cam, const RtbRenderOptions* opt) 
 // Core: enqueue the kernels for samples [begin, begin+count) on `stream`.  Caller holds the lock.
 static int render_enqueue(RtbScene* scene, const RtbCamera* cam, const RtbRenderOptions* opt, uint32_t begin,
                           uint32_t count, float* d_accum, cudaStream_t stream, LaunchInfo* info) {
+    // the megakernel in reference order walks the (min, max) layout built at creation; everything else a per-octant one
+    if (opt->traversal != RTB_TRAVERSAL_REFERENCE || opt->integrator == RTB_INTEGRATOR_WAVEFRONT) {
+        const int rc = ensure_layouts(scene, opt->traversal);
+        if (rc != RTB_OK) return rc;
+    }
     RenderParams p{};
     p.scene = scene->dev;
     p.cam = lower_camera(cam);

@@ -57,6 +57,21 @@ struct DevQuad {  // Quad fields incl. the ones Quad.init derives (src/objects.z
     float4 w;         // w.xyz
 };
 
+// One entry per hittable (top-level objects AND the children of wrappers), for the general instancing path (hit_any):
+//   sphere / quad / box / constant_medium : slot = quad-table slot of a quad / box header (spheres read prims[])
+//   translate : child, p = offset            rotate_y : child, p = (sin_theta, cos_theta)
+//   list      : child = first member, count  medium_of : child = boundary, p.x = neg_inv_density
+struct DevInst {
+    uint32_t type, child, count, slot;
+    float4 p;
+};
+// What a leaf test of a complex object may need; passed by value through the traversal functions.
+struct ComplexTables {
+    const DevQuad* quads;
+    const DevInst* insts;
+    const float4* prims;
+};
+
 struct DevScene {
     const float4* nodes;  // 2 per node: reference order, bounds as (min, max)
     // Per-octant layouts for the wavefront integrator, [mode][octant][2 * n_nodes], bounds pre-swapped
@@ -95,9 +110,11 @@ struct DevScene {
     const DevPerlin* perlins;
     const DevImage* images;
     const DevQuad* quads;
+    const DevInst* insts;  // n_objects entries
     uint32_t has_quads;
     uint32_t n_perlins;
 };
+__device__ __forceinline__ ComplexTables complex_tables(const DevScene& sc) { return ComplexTables{sc.quads, sc.insts, sc.prims}; }
 
 struct DevCamera {
     float3 center, pixel00, du, dv, ddu, ddv, background;
@@ -280,7 +297,7 @@ __device__ __forceinline__ bool slab_miss(float4 f0, float4 f1, float3 o, float 
 // A box instance = Translate(RotateY(createBox(a, b, mat), angle), offset) (src/objects.zig:308-443, :510-532),
 // stored in the quad table as a header entry {q_d = (offset.xyz, sin_theta), u.x = cos_theta} followed by
 // the 6 quads createBox makes, in its order.  Leaf record of a complex object: f1.x = bits(subtype).
-enum : uint32_t { COMPLEX_QUAD = 0u, COMPLEX_BOX = 1u, COMPLEX_MEDIUM = 2u };
+enum : uint32_t { COMPLEX_QUAD = 0u, COMPLEX_BOX = 1u, COMPLEX_MEDIUM = 2u, COMPLEX_GENERIC = 3u };
 
 // Translate.hit (:331-335) then RotateY.hit (:410-421): the ray in the box's own frame.
 __device__ __forceinline__ DRay box_local_ray(const DRay& r, const DevQuad& hdr) {
@@ -338,11 +355,23 @@ __device__ __forceinline__ bool medium_root(const DRay& r, const DevQuad* __rest
     return true;
 }
 
-// Leaf test of a complex object (quad, box instance or constant medium); f1 = {bits(subtype), -, -, bits(slot)}.
-__device__ __forceinline__ bool complex_root(const DRay& r, const DevQuad* __restrict__ quads, float4 f1, float t_min,
+// The general instancing path (src/objects.zig:264-443): Translate / RotateY / HittableList / ConstantMedium wrapping
+// ANY hittable, evaluated recursively like the reference's `inline else => |object| object.hit(r, ray_t)`.
+struct AnyHit {
+    float3 p, normal;
+    float t, u, v;
+    uint32_t prim;  // the hittable whose material shades this hit
+    bool front_face;
+};
+static __device__ __noinline__ bool hit_any(ComplexTables ct, uint32_t idx, DRay r, float t_min, float t_max, AnyHit* h,
+                                            RngKey key, uint32_t segment);
+
+// Leaf test of a complex object (quad, box instance, constant medium, or a general wrapper);
+// f1 = {bits(subtype), -, -, bits(slot)} (slot = the object's own index for COMPLEX_GENERIC).
+__device__ __forceinline__ bool complex_root(const DRay& r, ComplexTables ct, float4 f1, float t_min,
                                              float t_max, float& t_out, const RngKey& key, uint32_t segment,
                                              uint32_t object) {
-    const DevQuad* __restrict__ entry = quads + __float_as_uint(f1.w);
+    const DevQuad* __restrict__ entry = ct.quads + __float_as_uint(f1.w);
     const uint32_t subtype = __float_as_uint(f1.x);
     float alpha, beta;
     if (subtype == COMPLEX_BOX) {
@@ -350,6 +379,12 @@ __device__ __forceinline__ bool complex_root(const DRay& r, const DevQuad* __res
         return box_root(r, entry, t_min, t_max, t_out, face, alpha, beta);
     }
     if (subtype == COMPLEX_MEDIUM) return medium_root(r, entry, t_min, t_max, key, segment, object, t_out);
+    if (subtype == COMPLEX_GENERIC) {
+        AnyHit h;
+        if (!hit_any(ct, object, r, t_min, t_max, &h, key, segment)) return false;
+        t_out = h.t;
+        return true;
+    }
     return quad_root(r, entry[0], t_min, t_max, t_out, alpha, beta);
 }
 
@@ -424,7 +459,7 @@ __device__ __forceinline__ bool sphere_root_a(float3 o, float3 d, float a, float
 extern __shared__ float4 rtb_smem_nodes[];
 
 template <bool COUNT, bool QUADS, bool SMEM, bool FMA = false>
-__device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ nodes, const DevQuad* __restrict__ quads,
+__device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ nodes, ComplexTables quads,
                                                    float3 o, float3 d, float time, float inv_x, float inv_y,
                                                    float inv_z, float t_min, float t_max, uint32_t& n_box,
                                                    uint32_t& n_obj, uint32_t smem_base = 0u, RngKey key = RngKey{},
@@ -569,7 +604,7 @@ __device__ __forceinline__ __half2 packed_interval(float t_min, float t_max, flo
 // Walk over one octant's packed layout.  SMEM: `smem_base` is the shared-window address of the staged copy, whose skip
 // links are addresses (rewritten while staging); otherwise `slots` is the octant's array and the links are slot indices.
 template <bool COUNT, bool QUADS, bool SMEM>
-__device__ __forceinline__ Nearest traverse_packed(const uint4* __restrict__ slots, const DevQuad* __restrict__ quads,
+__device__ __forceinline__ Nearest traverse_packed(const uint4* __restrict__ slots, ComplexTables quads,
                                                    float3 o, float3 d, float time, const PackedRay& pr, float t_min,
                                                    float t_max, uint32_t& n_box, uint32_t& n_obj,
                                                    uint32_t smem_base = 0u, RngKey key = RngKey{},
@@ -645,7 +680,7 @@ __device__ __forceinline__ Nearest traverse_packed(const uint4* __restrict__ slo
 //     so ties go to the DFS-earlier object, as in `hit_record_right orelse hit_record_left`.
 template <bool COUNT, bool QUADS>
 __device__ __forceinline__ Nearest traverse_reference(const float4* __restrict__ nodes, uint32_t n_nodes,
-                                                      const DevQuad* __restrict__ quads, const DRay& r, float t_min,
+                                                      ComplexTables quads, const DRay& r, float t_min,
                                                       float t_max, uint32_t& n_box, uint32_t& n_obj,
                                                       RngKey key = RngKey{}, uint32_t segment = 1u) {
     Nearest best;
@@ -704,12 +739,26 @@ __device__ __forceinline__ void sphere_uv(float3 p, float& u, float& v) {
 // The part of Sphere.hit / Quad.hit after the root is accepted (src/objects.zig:139-147, :250-260),
 // evaluated once for the nearest hit instead of once per candidate.
 template <bool QUADS, bool WANT_UV>
-__device__ __forceinline__ DHit finish_hit_rec(float4 f0, float4 f1, const DevQuad* __restrict__ quads, const DRay& r,
-                                               float t) {
+__device__ __forceinline__ DHit finish_hit_rec(float4 f0, float4 f1, ComplexTables ct, const DRay& r,
+                                               float t, const RngKey& key = RngKey{}, uint32_t segment = 1u,
+                                               uint32_t* prim_out = nullptr) {
+    const DevQuad* __restrict__ quads = ct.quads;
     DHit h;
     const uint32_t meta = __float_as_uint(f0.w);
     const uint32_t kind = meta >> 30;
     h.object = meta & RTB_META_INDEX_MASK;
+    if (prim_out) *prim_out = h.object;
+    if (QUADS && kind == KIND_QUAD && __float_as_uint(f1.x) == COMPLEX_GENERIC) {
+        // a wrapper: evaluate the object again for its nearest hit (the same arithmetic gives the same t) and take
+        // the record the reference builds on the way out of the recursion
+        AnyHit a;
+        a.p = a.normal = f3(0.0f, 0.0f, 0.0f);
+        a.t = t; a.u = a.v = 0.0f; a.prim = h.object; a.front_face = false;
+        hit_any(ct, h.object, r, 0.001f, __int_as_float(0x7f800000), &a, key, segment);
+        h.t = a.t; h.p = a.p; h.normal = a.normal; h.u = a.u; h.v = a.v; h.front_face = a.front_face;
+        if (prim_out) *prim_out = a.prim;
+        return h;
+    }
     h.t = t;
     h.p = r.o + splat3(t) * r.d;  // Ray.at, src/ray.zig:9-11
     h.u = 0.0f;
@@ -770,9 +819,118 @@ __device__ __forceinline__ DHit finish_hit_rec(float4 f0, float4 f1, const DevQu
 
 // Same, with the leaf record fetched from a node / prim array (2 float4 per entry).
 template <bool QUADS, bool WANT_UV>
-__device__ __forceinline__ DHit finish_hit(const float4* __restrict__ nodes, const DevQuad* __restrict__ quads,
-                                           const DRay& r, Nearest best) {
-    return finish_hit_rec<QUADS, WANT_UV>(nodes[2u * best.node], nodes[2u * best.node + 1u], quads, r, best.t);
+__device__ __forceinline__ DHit finish_hit(const float4* __restrict__ nodes, ComplexTables ct,
+                                           const DRay& r, Nearest best, const RngKey& key = RngKey{},
+                                           uint32_t segment = 1u) {
+    return finish_hit_rec<QUADS, WANT_UV>(nodes[2u * best.node], nodes[2u * best.node + 1u], ct, r, best.t, key, segment);
+}
+
+// hit_any: Hittable.hit on any entry of the hittable table (src/objects.zig:49-53), recursive like the reference.
+// Every level follows its reference function; t values are the primitives' own (the transforms do not scale t).
+static __device__ __noinline__ bool hit_any(ComplexTables ct, uint32_t idx, DRay r, float t_min, float t_max, AnyHit* h,
+                                            RngKey key, uint32_t segment) {
+    const DevInst in = ct.insts[idx];
+    const float inf = __int_as_float(0x7f800000);
+    switch (in.type) {
+        case RTB_HITTABLE_SPHERE: {  // Sphere.hit, :116-148
+            const float4 f0 = ct.prims[4u * (size_t)idx], f1 = ct.prims[4u * (size_t)idx + 1u];
+            const uint32_t kind = __float_as_uint(f0.w) >> 30;
+            const float3 c1 = f3(f0);
+            const float3 center = (kind == KIND_MOVING_SPHERE) ? c1 + splat3(r.time) * f3(f1) : c1;
+            float root;
+            if (!sphere_root(r, center, f1.w, t_min, t_max, root)) return false;
+            const DHit d = finish_hit_rec<false, true>(f0, f1, ct, r, root);
+            h->t = root; h->p = d.p; h->normal = d.normal; h->u = d.u; h->v = d.v; h->front_face = d.front_face;
+            h->prim = idx;
+            return true;
+        }
+        case RTB_HITTABLE_QUAD: {  // Quad.hit, :226-261
+            const DevQuad qd = ct.quads[in.slot];
+            float t, alpha, beta;
+            if (!quad_root(r, qd, t_min, t_max, t, alpha, beta)) return false;
+            h->t = t;
+            h->p = r.o + splat3(t) * r.d;
+            h->u = alpha;
+            h->v = beta;
+            const float3 n = f3(qd.normal);
+            h->front_face = dot3(r.d, n) < 0.0f;
+            h->normal = h->front_face ? n : -n;
+            h->prim = idx;
+            return true;
+        }
+        case RTB_HITTABLE_BOX: {  // the one-record box instance: same code as a top-level box
+            float t, alpha, beta;
+            uint32_t face;
+            if (!box_root(r, ct.quads + in.slot, t_min, t_max, t, face, alpha, beta)) return false;
+            const float4 f0 = ct.prims[4u * (size_t)idx], f1 = ct.prims[4u * (size_t)idx + 1u];
+            const DHit d = finish_hit_rec<true, true>(f0, f1, ct, r, t);
+            h->t = t; h->p = d.p; h->normal = d.normal; h->u = d.u; h->v = d.v; h->front_face = d.front_face;
+            h->prim = idx;
+            return true;
+        }
+        case RTB_HITTABLE_CONSTANT_MEDIUM: {
+            float t;
+            if (!medium_root(r, ct.quads + in.slot, t_min, t_max, key, segment, idx, t)) return false;
+            h->t = t; h->p = r.o + splat3(t) * r.d; h->normal = f3(1.0f, 0.0f, 0.0f); h->u = h->v = 0.0f;
+            h->front_face = true;
+            h->prim = idx;
+            return true;
+        }
+        case RTB_HITTABLE_TRANSLATE: {  // Translate.hit, :327-345
+            const float3 offset = f3(in.p);
+            DRay moved = r;
+            moved.o = r.o - offset;
+            if (!hit_any(ct, in.child, moved, t_min, t_max, h, key, segment)) return false;
+            h->p = h->p + offset;
+            return true;
+        }
+        case RTB_HITTABLE_ROTATE_Y: {  // RotateY.hit, :404-442
+            const float sin_theta = in.p.x, cos_theta = in.p.y;
+            DRay rot = r;
+            rot.o = f3(cos_theta * r.o.x - sin_theta * r.o.z, r.o.y, sin_theta * r.o.x + cos_theta * r.o.z);
+            rot.d = f3(cos_theta * r.d.x - sin_theta * r.d.z, r.d.y, sin_theta * r.d.x + cos_theta * r.d.z);
+            if (!hit_any(ct, in.child, rot, t_min, t_max, h, key, segment)) return false;
+            const float3 p = h->p, n = h->normal;
+            h->p = f3(cos_theta * p.x + sin_theta * p.z, p.y, -sin_theta * p.x + cos_theta * p.z);
+            h->normal = f3(cos_theta * n.x + sin_theta * n.z, n.y, -sin_theta * n.x + cos_theta * n.z);
+            return true;
+        }
+        case RTB_HITTABLE_LIST: {  // HittableList.hit, :286-304
+            bool hit = false;
+            float closest = t_max;
+            for (uint32_t k = 0; k < in.count; ++k) {
+                AnyHit c;
+                if (hit_any(ct, in.child + k, r, t_min, closest, &c, key, segment)) {
+                    closest = c.t;
+                    *h = c;
+                    hit = true;
+                }
+            }
+            return hit;
+        }
+        case RTB_HITTABLE_MEDIUM_OF: {  // ConstantMedium.hit, :462-507, over any boundary
+            AnyHit r1, r2;
+            if (!hit_any(ct, in.child, r, -inf, inf, &r1, key, segment)) return false;
+            if (!hit_any(ct, in.child, r, r1.t + 0.0001f, inf, &r2, key, segment)) return false;
+            float t1 = r1.t, t2 = r2.t;
+            if (t1 < t_min) t1 = t_min;
+            if (t2 > t_max) t2 = t_max;
+            if (t1 >= t2) return false;
+            if (t1 < 0.0f) t1 = 0.0f;
+            const float ray_length = sqrtf(length_squared(r.d));
+            const float distance_inside_boundary = (t2 - t1) * ray_length;
+            const float hit_distance = in.p.x * logf(rng_block(key, segment, 0x40000000u + idx).x);
+            if (hit_distance > distance_inside_boundary) return false;
+            h->t = t1 + hit_distance / ray_length;
+            h->p = r.o + splat3(h->t) * r.d;
+            h->normal = f3(1.0f, 0.0f, 0.0f);
+            h->u = h->v = 0.0f;
+            h->front_face = true;
+            h->prim = idx;
+            return true;
+        }
+        default: return false;
+    }
 }
 
 // ------------------------------------------------------------------ textures
@@ -873,23 +1031,41 @@ struct ShadeResult {
     bool scatters;
 };
 
+__device__ __forceinline__ ShadeResult shade_hit(const DevScene& sc, const DHit& h, float4 m0, float4 m1, const DRay& r,
+                                                 const RngKey& key, uint32_t segment);
+
 // emitted + scatter for the nearest hit (src/camera.zig:194-196 -> src/material.zig:18-30).
 // `segment` (>= 1) keys this hit's RNG stream; block 0 word 3 is the dielectric reflectance draw.
 // `f0,f1` = the hit object's leaf record, `m0,m1` = its material record.
 template <bool QUADS>
 __device__ __forceinline__ ShadeResult shade_rec(const DevScene& sc, float4 f0, float4 f1, float4 m0, float4 m1,
                                                  const DRay& r, float t, const RngKey& key, uint32_t segment) {
+    const uint32_t tex_type = (__float_as_uint(m0.x) >> 8) & 0xffu;
+    DHit h;
+    if (QUADS && (__float_as_uint(f0.w) >> 30) == KIND_QUAD && __float_as_uint(f1.x) == COMPLEX_GENERIC) {
+        // a wrapper has no material of its own: shade with the material of the primitive that was hit inside it
+        uint32_t prim = 0u;
+        h = finish_hit_rec<QUADS, true>(f0, f1, complex_tables(sc), r, t, key, segment, &prim);
+        m0 = sc.prims[4u * (size_t)prim + 2u];
+        m1 = sc.prims[4u * (size_t)prim + 3u];
+        return shade_hit(sc, h, m0, m1, r, key, segment);
+    }
+    if (texture_needs_uv(tex_type))
+        h = finish_hit_rec<QUADS, true>(f0, f1, complex_tables(sc), r, t);
+    else
+        h = finish_hit_rec<QUADS, false>(f0, f1, complex_tables(sc), r, t);
+    return shade_hit(sc, h, m0, m1, r, key, segment);
+}
+
+// emitted + scatter once the hit record and the material record are known.
+__device__ __forceinline__ ShadeResult shade_hit(const DevScene& sc, const DHit& h, float4 m0, float4 m1, const DRay& r,
+                                                 const RngKey& key, uint32_t segment) {
     ShadeResult out;
     const TexTables tt{sc.textures, sc.perlins, sc.images};
     out.emitted = f3(0.0f, 0.0f, 0.0f);
     const uint32_t tag = __float_as_uint(m0.x);
     const uint32_t type = tag & 0xffu;
     const uint32_t tex_type = (tag >> 8) & 0xffu;
-    DHit h;
-    if (texture_needs_uv(tex_type))
-        h = finish_hit_rec<QUADS, true>(f0, f1, sc.quads, r, t);
-    else
-        h = finish_hit_rec<QUADS, false>(f0, f1, sc.quads, r, t);
     out.scattered.o = h.p;
     out.scattered.time = r.time;
     if (type == RTB_MAT_LAMBERTIAN) {  // src/material.zig:43-54

@@ -58,22 +58,22 @@ __global__ void __launch_bounds__(kCtaThreads) render_megakernel(const RenderPar
                 if (ORDERED && P.ordered == 3u) {  // RTB_TRAVERSAL_SAH16: packed half2 box nodes
                     const uint4* slots = P.scene.pk_nodes + (size_t)ray_octant_of_direction(ray.d) * P.scene.pk_slots;
                     const PackedRay pr = packed_ray_setup(P.scene, ray.o, ray.d);
-                    best = traverse_packed<COUNT, QUADS, false>(slots, P.scene.quads, ray.o, ray.d, ray.time, pr, 0.001f,
+                    best = traverse_packed<COUNT, QUADS, false>(slots, complex_tables(P.scene), ray.o, ray.d, ray.time, pr, 0.001f,
                                                                 __int_as_float(0x7f800000), n_box, n_obj, 0u, key, segment);
                 } else if (ORDERED) {
                     const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
                     const float4* oct =
                         P.scene.oct_nodes[P.ordered] + (size_t)ray_octant(ix, iy, iz) * 2u * (P.scene.oct_n_nodes[P.ordered] + 1u);
                     if (P.ordered == 2u)
-                        best = traverse_octant<COUNT, QUADS, false, true>(oct, P.scene.quads, ray.o, ray.d, ray.time, ix,
+                        best = traverse_octant<COUNT, QUADS, false, true>(oct, complex_tables(P.scene), ray.o, ray.d, ray.time, ix,
                                                                           iy, iz, 0.001f, __int_as_float(0x7f800000),
                                                                           n_box, n_obj, 0u, key, segment);
                     else
-                        best = traverse_octant<COUNT, QUADS, false>(oct, P.scene.quads, ray.o, ray.d, ray.time, ix, iy, iz,
+                        best = traverse_octant<COUNT, QUADS, false>(oct, complex_tables(P.scene), ray.o, ray.d, ray.time, ix, iy, iz,
                                                                     0.001f, __int_as_float(0x7f800000), n_box, n_obj, 0u,
                                                                     key, segment);
                 } else {
-                    best = traverse_reference<COUNT, QUADS>(nodes, P.scene.n_nodes, P.scene.quads, ray, 0.001f,
+                    best = traverse_reference<COUNT, QUADS>(nodes, P.scene.n_nodes, complex_tables(P.scene), ray, 0.001f,
                                                             __int_as_float(0x7f800000), n_box, n_obj, key, segment);
                 }
                 bool done;
@@ -196,19 +196,19 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     if (ORDERED && layout == 3u) {
         const uint4* slots = scene.pk_nodes + (size_t)ray_octant_of_direction(r.d) * scene.pk_slots;
         const PackedRay pr = packed_ray_setup(scene, r.o, r.d);
-        best = traverse_packed<true, QUADS, false>(slots, scene.quads, r.o, r.d, r.time, pr, rr.t_min, rr.t_max, n_box,
+        best = traverse_packed<true, QUADS, false>(slots, complex_tables(scene), r.o, r.d, r.time, pr, rr.t_min, rr.t_max, n_box,
                                                    n_obj, 0u, qkey, 1u);
     } else if (ORDERED) {
         const float ix = 1.0f / r.d.x, iy = 1.0f / r.d.y, iz = 1.0f / r.d.z;
         const float4* oct = scene.oct_nodes[layout] + (size_t)ray_octant(ix, iy, iz) * 2u * (scene.oct_n_nodes[layout] + 1u);
         if (layout == 2u)
-            best = traverse_octant<true, QUADS, false, true>(oct, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min,
+            best = traverse_octant<true, QUADS, false, true>(oct, complex_tables(scene), r.o, r.d, r.time, ix, iy, iz, rr.t_min,
                                                              rr.t_max, n_box, n_obj, 0u, qkey, 1u);
         else
-            best = traverse_octant<true, QUADS, false>(oct, scene.quads, r.o, r.d, r.time, ix, iy, iz, rr.t_min, rr.t_max,
+            best = traverse_octant<true, QUADS, false>(oct, complex_tables(scene), r.o, r.d, r.time, ix, iy, iz, rr.t_min, rr.t_max,
                                                        n_box, n_obj, 0u, qkey, 1u);
     } else {
-        best = traverse_reference<true, QUADS>(scene.nodes, scene.n_nodes, scene.quads, r, rr.t_min, rr.t_max, n_box,
+        best = traverse_reference<true, QUADS>(scene.nodes, scene.n_nodes, complex_tables(scene), r, rr.t_min, rr.t_max, n_box,
                                                n_obj, qkey, 1u);
     }
     RtbHit h;
@@ -220,8 +220,9 @@ __global__ void __launch_bounds__(256) trace_kernel(const DevScene scene, const 
     h.u = h.v = 0.0f;
     if (best.node != 0xffffffffu) {
         const DHit d = ORDERED ? finish_hit_rec<QUADS, true>(scene.prims[4u * (size_t)best.node],
-                                                             scene.prims[4u * (size_t)best.node + 1u], scene.quads, r, best.t)
-                               : finish_hit<QUADS, true>(scene.nodes, scene.quads, r, best);
+                                                             scene.prims[4u * (size_t)best.node + 1u], complex_tables(scene), r, best.t,
+                                                             qkey, 1u)
+                               : finish_hit<QUADS, true>(scene.nodes, complex_tables(scene), r, best, qkey, 1u);
         h.object = (int32_t)d.object;
         h.front_face = d.front_face ? 1u : 0u;
         h.t = d.t;

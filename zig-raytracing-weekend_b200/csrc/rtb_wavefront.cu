@@ -292,12 +292,12 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
             Nearest best;
             if (PACKED) {
                 const PackedRay pr = packed_ray_setup(P.R.scene, o, d);
-                best = traverse_packed<COUNT, QUADS, SMEM_NODES>(reinterpret_cast<const uint4*>(nodes), P.R.scene.quads, o,
+                best = traverse_packed<COUNT, QUADS, SMEM_NODES>(reinterpret_cast<const uint4*>(nodes), complex_tables(P.R.scene), o,
                                                                  d, a.w, pr, 0.001f, __int_as_float(0x7f800000), n_box,
                                                                  n_obj, smem_base, key, P.segment);
             } else {
                 best = traverse_octant<COUNT, QUADS, SMEM_NODES, SLAB == kSlabFma>(
-                    nodes, P.R.scene.quads, o, d, a.w, 1.0f / d.x, 1.0f / d.y, 1.0f / d.z, 0.001f,
+                    nodes, complex_tables(P.R.scene), o, d, a.w, 1.0f / d.x, 1.0f / d.y, 1.0f / d.z, 0.001f,
                     __int_as_float(0x7f800000), n_box, n_obj, smem_base, key, P.segment);
             }
             if (best.node != 0xffffffffu) cls = P.R.scene.object_class[best.node];
@@ -690,12 +690,12 @@ __global__ void __launch_bounds__(256) wf_tail(const WfParams P) {
                 const uint4* __restrict__ slots =
                     reinterpret_cast<const uint4*>(layouts) + (size_t)ray_octant_of_direction(ray.d) * oct_stride;
                 const PackedRay pr = packed_ray_setup(P.R.scene, ray.o, ray.d);
-                best = traverse_packed<COUNT, QUADS, false>(slots, P.R.scene.quads, ray.o, ray.d, ray.time, pr, 0.001f,
+                best = traverse_packed<COUNT, QUADS, false>(slots, complex_tables(P.R.scene), ray.o, ray.d, ray.time, pr, 0.001f,
                                                             __int_as_float(0x7f800000), n_box, n_obj, 0u, key, segment);
             } else {
                 const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
                 const float4* __restrict__ nodes = layouts + (size_t)ray_octant(ix, iy, iz) * oct_stride;
-                best = traverse_octant<COUNT, QUADS, false, SLAB == kSlabFma>(nodes, P.R.scene.quads, ray.o, ray.d, ray.time,
+                best = traverse_octant<COUNT, QUADS, false, SLAB == kSlabFma>(nodes, complex_tables(P.R.scene), ray.o, ray.d, ray.time,
                                                                              ix, iy, iz, 0.001f, __int_as_float(0x7f800000),
                                                                              n_box, n_obj, 0u, key, segment);
             }

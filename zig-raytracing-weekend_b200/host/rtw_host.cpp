@@ -262,6 +262,50 @@ Hittable Translate::init(const Hittable& box, Vec3 offset) {  // objects.zig:314
     return h;
 }
 
+// ---- general instancing: wrappers around any hittable --------------------------------------------------------
+Hittable HittableList::init(const std::vector<Hittable>& objects) {  // objects.zig:269-277
+    Hittable h;
+    h.type = RTB_HITTABLE_LIST;
+    Aabb box;  // Aabb{}: [0, 0]^3 — the reference's list box always contains the origin
+    for (const Hittable& o : objects) {
+        h.children.push_back(o);
+        box = Aabb::fromBoxes(box, o.bounding_box);
+    }
+    h.bounding_box = box;
+    return h;
+}
+Hittable TranslateAny::init(const Hittable& obj, Vec3 offset) {  // objects.zig:314-319, aabb.zig:51-57
+    Hittable h;
+    h.type = RTB_HITTABLE_TRANSLATE;
+    h.a = offset;
+    h.children.push_back(obj);
+    h.bounding_box.x = {obj.bounding_box.x.min + offset.x, obj.bounding_box.x.max + offset.x};
+    h.bounding_box.y = {obj.bounding_box.y.min + offset.y, obj.bounding_box.y.max + offset.y};
+    h.bounding_box.z = {obj.bounding_box.z.min + offset.z, obj.bounding_box.z.max + offset.z};
+    return h;
+}
+Hittable RotateYAny::init(const Hittable& obj, float angle_degrees) {  // objects.zig:354-397
+    Hittable flat = obj;  // reuse RotateY::init's box arithmetic (it only reads the bounding box and the angle)
+    flat.children.clear();
+    const Hittable r = RotateY::init(flat, angle_degrees);
+    Hittable h;
+    h.type = RTB_HITTABLE_ROTATE_Y;
+    h.sin_theta = r.sin_theta;
+    h.cos_theta = r.cos_theta;
+    h.bounding_box = r.bounding_box;
+    h.children.push_back(obj);
+    return h;
+}
+Hittable ConstantMediumOf::initFromColor(const Hittable& boundary, float d, Vec3 c) {  // objects.zig:450-460
+    Hittable h;
+    h.type = RTB_HITTABLE_MEDIUM_OF;
+    h.radius = -1.0f / d;
+    h.mat = Isotropic::fromColor(c);
+    h.bounding_box = boundary.bounding_box;
+    h.children.push_back(boundary);
+    return h;
+}
+
 Material Isotropic::init(const Texture& t) {
     Material m;
     m.type = RTB_MAT_ISOTROPIC;
@@ -397,18 +441,16 @@ std::unique_ptr<LoweredScene> World::lower() const {
         ls->textures.push_back(r);
         return (uint32_t)ls->textures.size() - 1;
     };
-    for (const Hittable& h : objects) {
-        RtbMaterial m{};
-        m.type = h.mat.type;
-        put3(m.albedo, h.mat.albedo);
-        m.fuzz = h.mat.fuzz;
-        m.ir = h.mat.ir;
-        if (m.type == RTB_MAT_LAMBERTIAN || m.type == RTB_MAT_DIFFUSE_LIGHT || m.type == RTB_MAT_ISOTROPIC)
-            m.texture = lowerTexture(h.mat.texture);
-        ls->materials.push_back(m);
+    // Top-level objects keep their position in the list (= the object index BVH leaves and rtb_trace_rays use);
+    // the objects wrapped by Translate / RotateY / HittableList / ConstantMedium follow, each wrapper's children
+    // contiguous and after the wrapper itself (include/rtb.h).
+    std::vector<const Hittable*> order;
+    for (const Hittable& h : objects) order.push_back(&h);
+    ls->hittables.resize(order.size());
+    for (size_t i = 0; i < order.size(); ++i) {   // `order` grows while children are appended
+        const Hittable& h = *order[i];
         RtbHittable r{};
         r.type = h.type;
-        r.material = (uint32_t)ls->materials.size() - 1;
         r.is_moving = h.is_moving ? 1u : 0u;
         r.radius = h.radius;
         r.sin_theta = h.sin_theta;
@@ -416,7 +458,25 @@ std::unique_ptr<LoweredScene> World::lower() const {
         put3(r.a, h.a);
         put3(r.b, h.b);
         put3(r.c, h.c);
-        ls->hittables.push_back(r);
+        const bool has_material = h.type != RTB_HITTABLE_TRANSLATE && h.type != RTB_HITTABLE_ROTATE_Y && h.type != RTB_HITTABLE_LIST;
+        if (has_material) {
+            RtbMaterial m{};
+            m.type = h.mat.type;
+            put3(m.albedo, h.mat.albedo);
+            m.fuzz = h.mat.fuzz;
+            m.ir = h.mat.ir;
+            if (m.type == RTB_MAT_LAMBERTIAN || m.type == RTB_MAT_DIFFUSE_LIGHT || m.type == RTB_MAT_ISOTROPIC)
+                m.texture = lowerTexture(h.mat.texture);
+            ls->materials.push_back(m);
+            r.material = (uint32_t)ls->materials.size() - 1;
+        }
+        if (!h.children.empty()) {
+            r.child = (uint32_t)order.size();
+            if (h.type == RTB_HITTABLE_LIST) r.material = (uint32_t)h.children.size();
+            for (const Hittable& c : h.children) order.push_back(&c);
+            ls->hittables.resize(order.size());
+        }
+        ls->hittables[i] = r;
     }
     // Pre-order walk with an explicit stack (the million-sphere tree is only ~21 deep, but the
     // Zig shim walks arbitrary pointer graphs the same way).

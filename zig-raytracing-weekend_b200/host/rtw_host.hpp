@@ -131,6 +131,9 @@ struct Hittable {  // src/objects.zig:39-47 (sphere, quad, and list/rotate_y/tra
     bool rotated = false, translated = false;
     Material mat;
     Aabb bounding_box;
+    // General instancing (objects.zig:264-443): a Translate / RotateY / HittableList / ConstantMedium that wraps
+    // ANYTHING holds its wrapped objects by value here (the reference copies `obj` into allocator.create(Hittable)).
+    std::vector<Hittable> children;
     const Aabb& boundingBox() const { return bounding_box; }
 };
 struct Sphere {
@@ -150,6 +153,20 @@ struct RotateY {
 };
 struct Translate {
     static Hittable init(const Hittable& box, Vec3 offset);  // src/objects.zig:314-319
+};
+// The general forms.  Translate::init / RotateY::init above keep a createBox-derived box as ONE flat record (the fast
+// path HEAD's scenes use); these wrap any hittable, any number of times, in any order.
+struct HittableList {  // src/objects.zig:264-305; the list's box starts as Aabb{} = the origin (:266, :274-277)
+    static Hittable init(const std::vector<Hittable>& objects);
+};
+struct TranslateAny {
+    static Hittable init(const Hittable& obj, Vec3 offset);  // src/objects.zig:314-319
+};
+struct RotateYAny {
+    static Hittable init(const Hittable& obj, float angle_degrees);  // src/objects.zig:354-397
+};
+struct ConstantMediumOf {
+    static Hittable initFromColor(const Hittable& boundary, float d, Vec3 c);  // src/objects.zig:450-460
 };
 struct Isotropic {
     static Material init(const Texture& t);  // src/material.zig:131-133

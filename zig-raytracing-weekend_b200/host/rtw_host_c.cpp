@@ -13,6 +13,7 @@ struct RtwWorld {
     World world;
     std::unique_ptr<LoweredScene> lowered;
     std::map<uint64_t, Texture> noise_by_seed;
+    std::vector<Hittable> detached;  // objects built by rtw_obj_* and not (yet) attached to the world list
     bool built = false;
 };
 
@@ -180,6 +181,63 @@ extern "C" int rtw_world_add_medium(RtwWorld* w, const float a[3], const float b
     if (rotate) box = RotateY::init(box, angle_degrees);
     if (offset_or_null) box = Translate::init(box, V(offset_or_null));
     w->world.objects.push_back(ConstantMedium::initFromColor(box, density, V(color)));
+    return RTB_OK;
+}
+
+// ---- detached objects + general wrappers ------------------------------------------------------------------------
+static int detach(RtwWorld* w, const Hittable& h, uint32_t* handle_out) {
+    if (!handle_out) return RTB_ERR_INVALID_ARGUMENT;
+    w->detached.push_back(h);
+    *handle_out = (uint32_t)w->detached.size() - 1u;
+    return RTB_OK;
+}
+extern "C" int rtw_obj_sphere(RtwWorld* w, const float c1[3], const float* c2, float radius, const RtwMaterialSpec* spec,
+                              uint32_t* handle_out) {
+    if (!w || w->built || !c1) return RTB_ERR_INVALID_ARGUMENT;
+    Material m;
+    const int rc = make_material(w, spec, &m);
+    if (rc != RTB_OK) return rc;
+    return detach(w, c2 ? Sphere::initMoving(V(c1), V(c2), radius, m) : Sphere::init(V(c1), radius, m), handle_out);
+}
+extern "C" int rtw_obj_quad(RtwWorld* w, const float q[3], const float u[3], const float v[3], const RtwMaterialSpec* spec,
+                            uint32_t* handle_out) {
+    if (!w || w->built || !q || !u || !v) return RTB_ERR_INVALID_ARGUMENT;
+    Material m;
+    const int rc = make_material(w, spec, &m);
+    if (rc != RTB_OK) return rc;
+    return detach(w, Quad::init(V(q), V(u), V(v), m), handle_out);
+}
+extern "C" int rtw_obj_box(RtwWorld* w, const float a[3], const float b[3], const RtwMaterialSpec* spec, uint32_t* handle_out) {
+    if (!w || w->built || !a || !b) return RTB_ERR_INVALID_ARGUMENT;
+    Material m;
+    const int rc = make_material(w, spec, &m);
+    if (rc != RTB_OK) return rc;
+    return detach(w, createBox(V(a), V(b), m), handle_out);
+}
+extern "C" int rtw_obj_list(RtwWorld* w, const uint32_t* handles, uint32_t n, uint32_t* handle_out) {
+    if (!w || w->built || !handles || n == 0) return RTB_ERR_INVALID_ARGUMENT;
+    std::vector<Hittable> members;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (handles[k] >= w->detached.size()) return RTB_ERR_INVALID_ARGUMENT;
+        members.push_back(w->detached[handles[k]]);
+    }
+    return detach(w, HittableList::init(members), handle_out);
+}
+extern "C" int rtw_obj_translate(RtwWorld* w, uint32_t handle, const float offset[3], uint32_t* handle_out) {
+    if (!w || w->built || !offset || handle >= w->detached.size()) return RTB_ERR_INVALID_ARGUMENT;
+    return detach(w, TranslateAny::init(w->detached[handle], V(offset)), handle_out);
+}
+extern "C" int rtw_obj_rotate_y(RtwWorld* w, uint32_t handle, float angle_degrees, uint32_t* handle_out) {
+    if (!w || w->built || handle >= w->detached.size()) return RTB_ERR_INVALID_ARGUMENT;
+    return detach(w, RotateYAny::init(w->detached[handle], angle_degrees), handle_out);
+}
+extern "C" int rtw_obj_medium(RtwWorld* w, uint32_t boundary, float density, const float color[3], uint32_t* handle_out) {
+    if (!w || w->built || !color || !(density > 0) || boundary >= w->detached.size()) return RTB_ERR_INVALID_ARGUMENT;
+    return detach(w, ConstantMediumOf::initFromColor(w->detached[boundary], density, V(color)), handle_out);
+}
+extern "C" int rtw_world_add_object(RtwWorld* w, uint32_t handle) {
+    if (!w || w->built || handle >= w->detached.size()) return RTB_ERR_INVALID_ARGUMENT;
+    w->world.objects.push_back(w->detached[handle]);
     return RTB_OK;
 }
 
