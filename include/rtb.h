@@ -352,7 +352,7 @@ int rtb_render(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions*
  *     from the first batch at which bounce the paths have thinned out enough for the tail kernel (later renders of
  *     the same configuration reuse the value and do not block);
  *   * it keeps ray / hit / path-state queues on the device, allocated on first use and kept with the scene: 624 bytes
- *     per path in flight, 8 Mi paths per pipeline lane, 4 lanes = about 21 GB for frames that fill the batches (small
+ *     per path in flight, 4 Mi paths per pipeline lane, 8 lanes = about 21 GB for frames that fill the batches (small
  *     frames or few samples allocate proportionally less).  If an allocation fails it pipelines over fewer lanes (slower,
  *     same result) and only reports RTB_ERR_OUT_OF_MEMORY when not even one lane fits. */
 int rtb_render_device(RtbScene* scene, const RtbCamera* camera, const RtbRenderOptions* options,

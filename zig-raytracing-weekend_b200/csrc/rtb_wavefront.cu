@@ -44,8 +44,19 @@ constexpr uint32_t kChunk = 256;  // hit records per CTA pass of wf_shade
 #define RTB_EXTEND_THREADS 512
 #endif
 constexpr uint32_t kExtendThreads = RTB_EXTEND_THREADS;
+// CTAs of ONE wf_extend launch per SM when the layout is staged in shared memory.  Three fit (registers), and a launch
+// that takes all three slots was the default until r2r: but then every SM drains and refills at each kernel boundary
+// (a CTA walks a contiguous share of the chunks; shares of different octants take different times).  With one CTA per SM
+// per launch and twice as many lanes in flight, the three slots of an SM are held by launches of DIFFERENT batches at
+// different bounces, whose ends do not coincide: 3 530 -> 4 030 Mpaths/s on Book-1 (profiles/r2r_ab.log, r2s_ab.log;
+// capping the resident extend CTAs per SM to leave room for wf_shade instead made it slower, r2t_ab.log).
 #ifndef RTB_EXTEND_GRID_PER_SM
-#define RTB_EXTEND_GRID_PER_SM 3
+#define RTB_EXTEND_GRID_PER_SM 1
+#endif
+// The same for layouts that stay in global memory (the 1 M-sphere scene: an L2-latency-bound walk that wants every
+// warp it can get).
+#ifndef RTB_EXTEND_GRID_PER_SM_GLOBAL
+#define RTB_EXTEND_GRID_PER_SM_GLOBAL 3
 #endif
 #ifndef RTB_SHADE_GRID_PER_SM
 #define RTB_SHADE_GRID_PER_SM 8
@@ -86,10 +97,10 @@ struct WfLane {
 constexpr uint32_t kSurvivorSlots = 256;  // max_depth is a u8 in the reference (src/camera.zig:79)
 
 #ifndef RTB_WF_LANES
-#define RTB_WF_LANES 4
+#define RTB_WF_LANES 8
 #endif
 #ifndef RTB_WF_BATCH_LOG2
-#define RTB_WF_BATCH_LOG2 23
+#define RTB_WF_BATCH_LOG2 22
 #endif
 constexpr int kLanes = RTB_WF_LANES;
 
@@ -852,7 +863,7 @@ static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t
                              : wf_launch_extend_slab<COUNT, QUADS, kSlabExact>(P, smem_nodes, grid, stream);
 }
 
-// Batches of ~8 M paths are pipelined over kLanes streams.  After the first ~10 bounces a batch is a
+// Batches of ~4 M paths are pipelined over kLanes (8) streams.  After the first ~10 bounces a batch is a
 // thin, latency-bound tail (a few long paths; measured ~58 us per bounce for 40 bounces = 20 % of a
 // batch when run alone); on its own stream that tail overlaps the next batches' full-width bounces.
 // wf_accumulate calls are chained with events so every pixel still receives its samples in sample
@@ -881,7 +892,7 @@ static uint32_t wf_max_slots_per_sample() {
     static const uint32_t v = [] {
         const char* s = std::getenv("RTB_WF_MAX_SLOTS");
         const unsigned long long x = s ? std::strtoull(s, nullptr, 10) : 0ull;
-        return (x >= 256ull && x <= 0x1fffffffull) ? (uint32_t)x : (48u << 20);
+        return (x >= 256ull && x <= 0x1fffffffull) ? (uint32_t)x : (10u << 20);  // x 624 B x 8 lanes = 52 GB
     }();
     return v;
 }
@@ -911,7 +922,7 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     cudaError_t e = wf_init(st);
     if (e != cudaSuccess) return e;
     const uint32_t slots_per_sample = owned * kCtaThreads;
-    // Samples in flight per pixel and batch (624 B of queue/state per path slot: 5.2 GB per lane at 8 M).
+    // Samples in flight per pixel and batch (624 B of queue/state per path slot: 2.6 GB per lane at 4 Mi).
     const uint64_t target_paths = 1ull << RTB_WF_BATCH_LOG2;
     uint32_t B = (uint32_t)((target_paths + slots_per_sample - 1) / slots_per_sample);
     if (B < 1u) B = 1u;
@@ -975,7 +986,8 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         uint32_t grid = (cap + 255u) / 256u + kBins;  // chunks: every bin may end with a partial one
         if (grid > max_grid) grid = max_grid;
         uint32_t grid_e = (cap + kExtendThreads - 1u) / kExtendThreads + kBins;
-        if (grid_e > (uint32_t)st->sm_count * RTB_EXTEND_GRID_PER_SM) grid_e = (uint32_t)st->sm_count * RTB_EXTEND_GRID_PER_SM;
+        const uint32_t extend_per_sm = smem_nodes ? RTB_EXTEND_GRID_PER_SM : RTB_EXTEND_GRID_PER_SM_GLOBAL;
+        if (grid_e > (uint32_t)st->sm_count * extend_per_sm) grid_e = (uint32_t)st->sm_count * extend_per_sm;
         uint32_t grid_s = (cap + 255u) / 256u + kBins;
         if (grid_s > (uint32_t)st->sm_count * RTB_SHADE_GRID_PER_SM) grid_s = (uint32_t)st->sm_count * RTB_SHADE_GRID_PER_SM;
         // Where does the thin tail begin?  Known from the last render of this scene, or learned now: batch 0 runs
