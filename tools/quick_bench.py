@@ -20,6 +20,7 @@ ap.add_argument("--integrators", default="0,1")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--count", action="store_true")
 ap.add_argument("--traversal", type=int, default=0)
+ap.add_argument("--profile-last", action="store_true", help="cudaProfilerStart/Stop around the last repetition (ncu --replay-mode range)")
 a = ap.parse_args()
 
 import torch
@@ -40,7 +41,13 @@ for integ in [int(x) for x in a.integrators.split(",")]:
         acc.zero_()
         o = p.render_options(seed=1234, integrator=integ, traversal=a.traversal, flags=p.RTB_FLAG_COUNT_WORK if a.count else 0)
         torch.cuda.synchronize()
+        prof = a.profile_last and rep == a.reps - 1
+        if prof:
+            torch.cuda.cudart().cudaProfilerStart()
         st = scene.render_device(cam, o, acc.data_ptr(), 0)
+        if prof:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
         mp = st["n_paths"] / st["device_ms"] / 1e3
         extra = ""
         if a.count:

@@ -29,8 +29,10 @@
 
 #include <new>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace rtb {
 
@@ -113,7 +115,11 @@ struct WavefrontState {
     cudaEvent_t begin = nullptr;
     int sm_count = 0;
     bool ready = false;
+    // RTB_TIMELINE=<file>: per-warp residency records of the next render (development aid, tools/timeline.py)
+    uint4* timeline = nullptr;
+    uint32_t* timeline_count = nullptr;
 };
+constexpr uint32_t kTimelineCap = 24u << 20;
 
 struct WfParams {
     RenderParams R;
@@ -132,6 +138,40 @@ struct WfParams {
     uint32_t zero;              // always 0; only there to make an address opaque to ptxas (see traverse_octant)
     uint32_t* survivors;        // mapped host memory, [bounce] = rays entering that bounce (may be NULL)
     uint32_t perlin_smem;       // wf_shade: number of Perlin tables to stage in shared memory (0 = read them from global)
+    // RTB_TIMELINE (development aid, NULL otherwise): every warp appends {start ns lo, hi, duration ns, kind | sm << 8 |
+    // lane << 16 | bounce << 24} so that tools/timeline.py can reconstruct what was resident on each SM over time
+    uint4* timeline;
+    uint32_t* timeline_count;
+    uint32_t timeline_cap;
+    uint32_t timeline_tag;      // lane << 16 | bounce << 24
+};
+
+enum : uint32_t { TL_RAYGEN = 0u, TL_EXTEND = 1u, TL_SHADE = 2u, TL_TAIL = 3u };
+// The start time waits in shared memory (one slot per warp), not in a register the kernel would carry through its loops.
+struct TimelineScope {
+    __device__ __forceinline__ explicit TimelineScope(const WfParams& P) {
+        if (P.timeline && (threadIdx.x & 31u) == 0u) {
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            slot()[threadIdx.x >> 5] = t0;
+        }
+    }
+    static __device__ __forceinline__ unsigned long long* slot() {
+        __shared__ unsigned long long t0s[32];
+        return t0s;
+    }
+    __device__ __forceinline__ void finish(const WfParams& P, uint32_t kind) const {
+        if (P.timeline && (threadIdx.x & 31u) == 0u) {
+            unsigned long long t1;
+            uint32_t sm;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            const unsigned long long t0 = slot()[threadIdx.x >> 5];
+            const uint32_t at = atomicAdd(P.timeline_count, 1u);
+            if (at < P.timeline_cap)
+                P.timeline[at] = make_uint4((uint32_t)t0, (uint32_t)(t0 >> 32), (uint32_t)(t1 - t0), kind | (sm << 8) | P.timeline_tag);
+        }
+    }
 };
 
 __device__ __forceinline__ bool slot_pixel(const RenderParams& R, uint32_t r, uint32_t& pixel) {
@@ -193,6 +233,7 @@ __device__ __forceinline__ void chunk_map_init(ChunkMap& m, const uint32_t* coun
 }
 
 __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
+    const TimelineScope tl(P);
     const uint32_t total = P.slots_per_sample * P.batch_samples;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
@@ -221,6 +262,7 @@ __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
         }
         push_ray(P, ray, slot, push);
     }
+    tl.finish(P, TL_RAYGEN);
 }
 
 // One thread per ray, plain node loop over the octant's layout; the result goes to the hit queue of
@@ -232,6 +274,7 @@ enum : int { kSlabExact = 0, kSlabFma = 1, kSlabPacked = 2 };
 template <bool SMEM_NODES, bool COUNT, bool QUADS, int SLAB>
 __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_extend(const WfParams P) {
     __shared__ ChunkMap map;
+    const TimelineScope tl(P);
     constexpr bool PACKED = SLAB == kSlabPacked;
     const uint32_t layout = PACKED ? 2u : P.R.ordered;
     const uint32_t n_nodes = P.R.scene.oct_n_nodes[layout];
@@ -322,6 +365,7 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
         warp_add(&P.R.counters[1], n_box);
         warp_add(&P.R.counters[2], n_obj);
     }
+    tl.finish(P, TL_EXTEND);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -592,6 +636,7 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
 template <bool COUNT, bool QUADS>
 __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfParams P) {
     __shared__ ChunkMap map;
+    const TimelineScope tl(P);
     chunk_map_init(map, P.hit_count, kShadeClasses);
     const uint32_t total_chunks = map.first_chunk[kBins];
     uint32_t n_hits = 0;
@@ -655,6 +700,7 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
         push_ray(P, next, slot, push);
     }
     if (COUNT) warp_add(&P.R.counters[3], n_hits);
+    tl.finish(P, TL_SHADE);
 }
 
 // The thin tail of a batch.  After ~12 bounces of the Book-1 scene fewer than 1 % of the paths are alive, but the
@@ -665,6 +711,7 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
 template <bool COUNT, bool QUADS, int SLAB>
 __global__ void __launch_bounds__(256) wf_tail(const WfParams P) {
     __shared__ ChunkMap map;
+    const TimelineScope tl(P);
     chunk_map_init(map, P.count_in, kOctants);
     constexpr bool PACKED = SLAB == kSlabPacked;
     const uint32_t total_chunks = map.first_chunk[kBins];
@@ -732,6 +779,7 @@ __global__ void __launch_bounds__(256) wf_tail(const WfParams P) {
         warp_add(&P.R.counters[2], n_obj);
         warp_add(&P.R.counters[3], n_hits);
     }
+    tl.finish(P, TL_TAIL);
 }
 
 __global__ void __launch_bounds__(256) wf_accumulate(const WfParams P) {
@@ -777,6 +825,8 @@ void wavefront_destroy(WavefrontState* st) {
         if (ln.accumulated) cudaEventDestroy(ln.accumulated);
     }
     if (st->begin) cudaEventDestroy(st->begin);
+    cudaFree(st->timeline);
+    cudaFree(st->timeline_count);
     delete st;
 }
 
@@ -950,6 +1000,17 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     const uint32_t perlin_count = (perlin_smem_on && p.scene.n_perlins > 0u && p.scene.n_perlins <= 8u) ? p.scene.n_perlins : 0u;
     const size_t perlin_bytes = (size_t)perlin_count * sizeof(DevPerlin);
 
+    static const char* timeline_path = std::getenv("RTB_TIMELINE");
+    if (timeline_path && timeline_path[0] && !st->timeline) {
+        e = cudaMalloc(&st->timeline, (size_t)kTimelineCap * sizeof(uint4));
+        if (e == cudaSuccess) e = cudaMalloc(&st->timeline_count, sizeof(uint32_t));
+        if (e != cudaSuccess) return e;
+    }
+    if (st->timeline) {
+        e = cudaMemsetAsync(st->timeline_count, 0, sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return e;
+    }
+
     // fork: the lanes start after everything already queued on the caller's stream
     e = cudaEventRecord(st->begin, stream);
     for (int l = 0; l < lanes_used && e == cudaSuccess; ++l) e = cudaStreamWaitEvent(st->lanes[l].stream, st->begin, 0);
@@ -978,6 +1039,10 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         P.batch_begin = p.sample_begin + s0;
         P.batch_samples = nb;
         P.perlin_smem = perlin_count;
+        P.timeline = st->timeline;
+        P.timeline_count = st->timeline_count;
+        P.timeline_cap = kTimelineCap;
+        P.timeline_tag = (uint32_t)lane_id << 16;
         e = cudaMemsetAsync(ln.counts, 0, 4 * kBins * sizeof(uint32_t), ln.stream);
         if (e != cudaSuccess) return e;
         int cur = 0;
@@ -1009,6 +1074,7 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
         for (uint32_t bounce = 0; bounce < p.cam.max_depth; ++bounce) {
             P.in = ln.q[cur];
             P.count_in = ln.counts + cur * kBins;
+            P.timeline_tag = ((uint32_t)lane_id << 16) | ((bounce & 0xffu) << 24);
             if (tail_k != 0u && bounce >= tail_k) {  // everything still alive finishes in one launch
                 P.segment = bounce + 1u;
                 const uint32_t grid_t = (uint32_t)st->sm_count * 4u;
@@ -1068,6 +1134,20 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     e = cudaStreamWaitEvent(stream, st->lanes[prev_lane].accumulated, 0);
     if (e != cudaSuccess) return e;
     if (info) info->n_launches += launches;
+    if (st->timeline) {  // development aid: blocks, then writes the records of this render
+        e = cudaStreamSynchronize(stream);
+        uint32_t n = 0;
+        if (e == cudaSuccess) e = cudaMemcpy(&n, st->timeline_count, sizeof(n), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return e;
+        if (n > kTimelineCap) n = kTimelineCap;
+        std::vector<uint4> rec(n);
+        e = cudaMemcpy(rec.data(), st->timeline, (size_t)n * sizeof(uint4), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return e;
+        if (FILE* f = std::fopen(timeline_path, "wb")) {
+            std::fwrite(rec.data(), sizeof(uint4), n, f);
+            std::fclose(f);
+        }
+    }
     return cudaSuccess;
 }
 
