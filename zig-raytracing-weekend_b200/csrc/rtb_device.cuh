@@ -448,6 +448,31 @@ __device__ __forceinline__ bool sphere_root_a(float3 o, float3 d, float a, float
     return true;
 }
 
+// Packed FP32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 on a 64-bit register pair; each half rounds like the scalar op).
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // Traversal over one octant's threaded layout (DevScene::oct_nodes).  Visiting order is whatever the
 // host baked into the layout: the reference's left-then-right order (RTB_TRAVERSAL_REFERENCE) or
 // near-child-first for this octant (RTB_TRAVERSAL_ORDERED).  Nearest.node is the OBJECT index.
@@ -475,15 +500,26 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
     // SMEM: `i` is the node's 32-bit shared-window ADDRESS and the skip links of the staged copy are addresses too
     // (the staging loop rewrites them, see wf_extend), which saves the index -> address instruction of every visit.
     uint32_t i = SMEM ? smem_base : 0u;
+    // SMEM: the staged copy holds a node as (entry, exit) PAIRS per axis — {e.x, x.x, e.y, x.y} {e.z, x.z, meta, f1.w}
+    // (wf_extend shuffles while staging) — so that the six plane operations of a visit are three packed FP32
+    // instructions (sm_100 FADD2 / FMUL2 / FFMA2 on 64-bit register pairs) instead of six scalar ones.  Each half is the
+    // same IEEE round-to-nearest operation as the scalar form, and plane + (-o) is plane - o bit for bit, so the exact
+    // variant stays the reference's arithmetic; the kernel is bound by issue slots, not by the FP32 pipe.
+    const uint64_t IX = pack_f32x2(inv_x, inv_x), IY = pack_f32x2(inv_y, inv_y), IZ = pack_f32x2(inv_z, inv_z);
+    const uint64_t AX = FMA ? pack_f32x2(nox, nox) : pack_f32x2(-o.x, -o.x);
+    const uint64_t AY = FMA ? pack_f32x2(noy, noy) : pack_f32x2(-o.y, -o.y);
+    const uint64_t AZ = FMA ? pack_f32x2(noz, noz) : pack_f32x2(-o.z, -o.z);
     for (;;) {
         float4 f0, f1;
+        uint64_t px = 0, py = 0, pz = 0;
         if (SMEM) {
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(f0.x), "=f"(f0.y), "=f"(f0.z), "=f"(f0.w)
-                         : "r"(i));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];"
-                         : "=f"(f1.x), "=f"(f1.y), "=f"(f1.z), "=f"(f1.w)
-                         : "r"(i));
+            uint64_t mw;
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(px), "=l"(py) : "r"(i));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+16];" : "=l"(pz), "=l"(mw) : "r"(i));
+            unpack_f32x2(px, f0.x, f1.x);
+            unpack_f32x2(py, f0.y, f1.y);
+            unpack_f32x2(pz, f0.z, f1.z);
+            unpack_f32x2(mw, f0.w, f1.w);
         } else {
             f0 = nodes[2u * i];
             f1 = nodes[2u * i + 1u];
@@ -492,12 +528,40 @@ __device__ __forceinline__ Nearest traverse_octant(const float4* __restrict__ no
         const uint32_t meta = __float_as_uint(f0.w);
         if (meta < (1u << 30)) {  // KIND_INTERIOR: meta is the skip link
             if (COUNT) ++n_box;
-            const bool miss = FMA ? slab_miss_fma(f0, f1, inv_x, inv_y, inv_z, nox, noy, noz, t_min, best.t)
-                                  : slab_miss_preswapped(f0, f1, o, inv_x, inv_y, inv_z, t_min, best.t);
+            bool miss;
+            if (SMEM) {
+                float t0x, t1x, t0y, t1y, t0z, t1z;
+                if (FMA) {
+                    unpack_f32x2(fma_f32x2(px, IX, AX), t0x, t1x);
+                    unpack_f32x2(fma_f32x2(py, IY, AY), t0y, t1y);
+                    unpack_f32x2(fma_f32x2(pz, IZ, AZ), t0z, t1z);
+                } else {
+                    unpack_f32x2(mul_f32x2(add_f32x2(px, AX), IX), t0x, t1x);
+                    unpack_f32x2(mul_f32x2(add_f32x2(py, AY), IY), t0y, t1y);
+                    unpack_f32x2(mul_f32x2(add_f32x2(pz, AZ), IZ), t0z, t1z);
+                }
+                const float lo = fmaxf(max3f(t0x, t0y, t0z), t_min);
+                const float hi = fminf(min3f(t1x, t1y, t1z), best.t);
+                miss = hi <= lo;
+            } else {
+                miss = FMA ? slab_miss_fma(f0, f1, inv_x, inv_y, inv_z, nox, noy, noz, t_min, best.t)
+                           : slab_miss_preswapped(f0, f1, o, inv_x, inv_y, inv_z, t_min, best.t);
+            }
             i = miss ? meta : i + kStep;
         } else {
             if (meta == RTB_META_END) break;
             if (COUNT) ++n_obj;
+            if (SMEM) {
+                // the leaf's words are fetched again here: the slab path overwrites the pairs in place, and keeping a
+                // copy for this (rare) branch would cost three moves in every iteration of the node loop
+                uint64_t qx, qy, qz, qw;
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(qx), "=l"(qy) : "r"(i));
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+16];" : "=l"(qz), "=l"(qw) : "r"(i));
+                unpack_f32x2(qx, f0.x, f1.x);
+                unpack_f32x2(qy, f0.y, f1.y);
+                unpack_f32x2(qz, f0.z, f1.z);
+                unpack_f32x2(qw, f0.w, f1.w);
+            }
             const uint32_t kind = meta >> 30;
             if (!QUADS || kind != KIND_QUAD) {
                 const float3 c1 = f3(f0);

@@ -313,15 +313,22 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
         if (SMEM_NODES && oct != staged) {
             __syncthreads();
             // copy, turning the skip links (node indices) of interior nodes into shared-window addresses
-            for (uint32_t i = threadIdx.x; i < (uint32_t)oct_stride; i += blockDim.x) {
-                float4 v = nodes[i];
-                const uint32_t meta = __float_as_uint(v.w);
-                if (PACKED) {  // every slot: word 3 < 2^30 <=> box node (leaves set bit 30/31 in both of their slots)
+            if (PACKED) {
+                for (uint32_t i = threadIdx.x; i < (uint32_t)oct_stride; i += blockDim.x) {
+                    float4 v = nodes[i];
+                    const uint32_t meta = __float_as_uint(v.w);
+                    // every slot: word 3 < 2^30 <=> box node (leaves set bit 30/31 in both of their slots)
                     if (meta < (1u << 30)) v.w = __uint_as_float(smem_base + meta * 16u);
-                } else if ((i & 1u) == 0u && meta < (1u << 30)) {
-                    v.w = __uint_as_float(smem_base + meta * 32u);
+                    rtb_smem_nodes[i] = v;
                 }
-                rtb_smem_nodes[i] = v;
+            } else {  // a node becomes (entry, exit) pairs per axis for the packed-FP32 slab test (see traverse_octant)
+                for (uint32_t n = threadIdx.x; n < (uint32_t)oct_stride / 2u; n += blockDim.x) {
+                    const float4 f0 = nodes[2u * n], f1 = nodes[2u * n + 1u];
+                    uint32_t meta = __float_as_uint(f0.w);
+                    if (meta < (1u << 30)) meta = smem_base + meta * 32u;
+                    rtb_smem_nodes[2u * n] = make_float4(f0.x, f1.x, f0.y, f1.y);
+                    rtb_smem_nodes[2u * n + 1u] = make_float4(f0.z, f1.z, __uint_as_float(meta), f1.w);
+                }
             }
             __syncthreads();
             staged = oct;
