@@ -61,15 +61,19 @@ constexpr uint32_t kExtendThreads = RTB_EXTEND_THREADS;
 #define RTB_EXTEND_GRID_PER_SM_GLOBAL 3
 #endif
 #ifndef RTB_SHADE_GRID_PER_SM
-#define RTB_SHADE_GRID_PER_SM 8
+#define RTB_SHADE_GRID_PER_SM 5
 #endif
-// wf_shade is bound by DRAM latency (gathers of 32-byte records): 5 CTAs per SM (<= 48 registers) instead of the 4
-// that 64 registers allow measured +7 % on the whole step.
+// wf_shade's register budget.  Until r3b it was capped at 48 registers (5 CTAs per SM: it is bound by DRAM latency, and
+// when it ran alone on an SM the extra warps measured +7 %), at the price of 120 B of spills in its hot paths.  With
+// eight batches in flight the SM is shared with other launches anyway and issue slots are what the step is short of:
+// 80 registers (3 CTAs, no spills) measured +2.5 % on Book-1 and +3.3 % on the textured scene, 64 registers +1 %,
+// 128 registers -13 % (profiles/r3b_shade_occ_ab.log, r3c_shade_occ_ab.log); likewise 5 instead of 8 CTAs per SM
+// in its grid (+1 %).
 #ifndef RTB_EXTEND_CONTIGUOUS
 #define RTB_EXTEND_CONTIGUOUS 1
 #endif
 #ifndef RTB_SHADE_MINBLOCKS
-#define RTB_SHADE_MINBLOCKS 5
+#define RTB_SHADE_MINBLOCKS 3
 #endif
 #ifndef RTB_EXTEND_MINBLOCKS
 #define RTB_EXTEND_MINBLOCKS 3
