@@ -86,6 +86,8 @@ def parse_args():
     a = ap.parse_args()
     if a.lean:
         a.no_variants = a.no_parity = a.no_other_configs = a.no_reference_order = a.no_cpu_baseline = a.no_e2e = True
+        if a.integrator == "auto":  # no megakernel probe either (it would be 58 % of a serialised launch list)
+            a.integrator = "wavefront"
     base = {"book1": (1200, 500), "textured": (800, 256), "million": (3840, 64)}[a.scene]
     a.width = a.width or base[0]
     a.spp = a.spp or base[1]
