@@ -632,3 +632,29 @@ print("ok")
     env = dict(os.environ, RTB_EXTEND_STREAM=mode)
     out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
+
+
+def test_straggler_eviction_kernel_traces_the_same_walks(pkg, tmp_path):
+    """wf_extend_evict (RTB_EXTEND_EVICT=1; off by default because it measured slower) moves the last
+    few walking lanes of a warp to a shared-memory buffer and finishes them later as a dense group.  A straggler resumes
+    at the node it stopped at with the nearest hit it had, so the image AND every work counter equal the megakernel's."""
+    import subprocess
+    import sys
+    script = tmp_path / "evict.py"
+    script.write_text(f"""
+import importlib, sys
+import numpy as np
+sys.path.insert(0, {ROOT!r})
+pkg = importlib.import_module("zig-raytracing-weekend_b200")
+scene = pkg.Scene(pkg.World.book1())
+cam = pkg.book1_camera(400, 6, 50).init()
+a, _, sa = scene.render(cam, pkg.render_options(seed=9, integrator=1, traversal=3, flags=pkg.RTB_FLAG_COUNT_WORK))
+b, _, sb = scene.render(cam, pkg.render_options(seed=9, integrator=0, traversal=3, flags=pkg.RTB_FLAG_COUNT_WORK))
+assert np.array_equal(a, b), np.count_nonzero((a != b).any(axis=1))
+for k in ("n_rays", "n_hits", "n_box_tests", "n_object_tests"):
+    assert sa[k] == sb[k], (k, sa[k], sb[k])
+print("ok")
+""")
+    env = dict(os.environ, RTB_EXTEND_EVICT="1")
+    out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr

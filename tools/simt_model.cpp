@@ -97,7 +97,49 @@ int main(int argc, char** argv) {
             }
         }
     }
-    if (scheme != 2 && scheme != 3) for (int oc=0;oc<8;++oc) for (size_t w=0; w+32<=q[oc].size(); w+=32) {
+    if (scheme == 4) {
+        // while-while (K = 1) with STRAGGLER EVICTION: at a phase boundary (all lanes at a leaf or done) a warp with at
+        // most T lanes still walking writes them to a continuation queue and ends; the stragglers of an octant are
+        // regrouped into dense warps and finished by a second pass (no eviction there; argv[6] = 1: evict again).
+        const int C_EVICT = 24, C_RESUME = 30; const int again = argc > 6 ? atoi(argv[6]) : 0;
+        double evicted = 0, evictions = 0;
+        for (int oc=0;oc<8;++oc) {
+            const std::vector<Node>& N = L[oc];
+            std::vector<Lane> pool, nextpool;
+            for (size_t w=0; w+32<=q[oc].size(); w+=32) for (int t=0;t<32;++t){ Lane l; l.r=q[oc][w+t]; for(int k=0;k<3;++k) l.inv[k]=1.0f/l.r.d[k];
+                l.a=l.r.d[0]*l.r.d[0]+l.r.d[1]*l.r.d[1]+l.r.d[2]*l.r.d[2]; l.i=0; l.done=false; l.best=INFINITY; l.obj=-1; l.np=0; l.visits=l.leaves=0; pool.push_back(l); nrays+=1; }
+            for (int pass=0; !pool.empty(); ++pass) {
+                const bool may_evict = pass == 0 || (again && pass < 4);
+                for (size_t w=0; w<pool.size(); w+=32) {
+                    const int nl = (int)std::min<size_t>(32, pool.size()-w); Lane* ln=&pool[w];
+                    if (pass) cost += C_RESUME;
+                    for(;;){
+                        int alive=0; for(int t=0;t<nl;++t) if(!ln[t].done) ++alive; if(!alive) break;
+                        if (may_evict && alive <= T && alive < nl) { for(int t=0;t<nl;++t) if(!ln[t].done){ nextpool.push_back(ln[t]); ln[t].done=true; ++evicted; } cost += C_EVICT; ++evictions; break; }
+                        outer++;
+                        for(;;){ int act=0; for (int t=0;t<nl;++t){ Lane& l=ln[t]; if (l.done||l.np>=1) continue; ++act; const Node& n=N[l.i]; uint32_t m=fb(n.f[3]);
+                                if (m < (1u<<30)) { ++l.visits; l.i = slab_miss(n,l,l.best)? m : l.i+1; }
+                                else if (m==0xffffffffu) { l.done=true; }
+                                else { l.pend[l.np++]=l.i; l.i++; } }
+                            if(!act) break; warp_iters++; lane_iters+=act; cost += C_NODE; }
+                        { int lc=-1, cnt=0; for(int t=0;t<nl;++t){ Lane& l=ln[t]; if (l.np>0){ ++cnt; ++l.leaves; lc=std::max(lc,sphere(l,N[l.pend[0]])); l.np=0; } }
+                          if (lc>=0){ cost += (lc?C_LEAF1:C_LEAF0) + 4; leafphase++; leaflanes+=cnt; } }
+                        cost += 6 + 3;  // + the vote
+                    }
+                }
+                // a lane copied to nextpool keeps its visit counters; count the finished ones here
+                for (auto& l: pool) { bool moved=false; (void)moved; }
+                std::vector<Lane> fin; fin.swap(pool);
+                for (auto& l: fin) { visits += 0; (void)l; }
+                // visits/leaves: lanes evicted were copied WITH their counters, so only count lanes that were not copied
+                // (a copied lane was marked done right after the copy; its counters are counted when its copy finishes)
+                pool.swap(nextpool); nextpool.clear();
+                (void)fin;
+            }
+        }
+        printf("evicted %.1f %% of the rays in %.0f evictions\n", 100.0*evicted/nrays, evictions);
+    }
+    if (scheme != 2 && scheme != 3 && scheme != 4) for (int oc=0;oc<8;++oc) for (size_t w=0; w+32<=q[oc].size(); w+=32) {
         Lane ln[32];
         for (int t=0;t<32;++t){ Lane& l=ln[t]; l.r=q[oc][w+t]; for(int k=0;k<3;++k) l.inv[k]=1.0f/l.r.d[k];
             l.a=l.r.d[0]*l.r.d[0]+l.r.d[1]*l.r.d[1]+l.r.d[2]*l.r.d[2]; l.i=0; l.done=false; l.best=INFINITY; l.obj=-1; l.np=0; l.visits=l.leaves=0; }

@@ -17,7 +17,7 @@ L.tofile('/tmp/sim/layout.bin'); print("nodes",n.value)
 cam=pkg.book1_camera(1200,500,50).init()
 rng=np.random.default_rng(1)
 # camera rays in tile order: pick random 32x... use 8x4 pixel blocks like the kernel's warps
-NW=700
+NW=4000
 rays=[]
 W,H=1200,675
 for w in range(NW):

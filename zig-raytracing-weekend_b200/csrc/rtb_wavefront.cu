@@ -380,6 +380,180 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// wf_extend_evict — wf_extend over the packed SAH16 layout with STRAGGLER EVICTION.
+//
+// The compiler turns the node loop into phases — every lane walks to its next leaf (or to the end), the warp
+// reconverges, the lanes at a leaf test it — and a warp stays until its longest walk has ended: on bounce rays the
+// slab loop runs ~78 times per warp for rays that need 23 visits (tools/simt_model.cpp on real Book-1 rays), 11-16 of
+// 32 lanes busy.  Refilling idle lanes was tried three times and lost to its per-visit overheads (DESIGN.md 5.14c,
+// 5.17).  This kernel does the opposite and pays nothing per visit: at a phase boundary — where the warp is converged
+// anyway — ONE vote counts the lanes still walking; once they are few (<= kEvictAt) they write their walk state
+// {ray, node address, nearest hit so far} into a 32-entry buffer the warp owns in shared memory and the warp moves on
+// to its next 32 rays.  When the buffer is nearly full its stragglers are finished together as one dense group (a
+// straggler resumes exactly where it stopped — same node, same nearest hit, the same per-ray constants recomputed from
+// the same ray — so every hit and every work counter is identical to wf_extend's).
+// MEASURED (profiles/r3g_evict_*.csv, r3f_evict_ab.log): on bounce 1 the node loop runs 14 % fewer times, exactly as
+// the SIMT model predicts (8.69 M instead of 10.09 M warp-level LDS), and 19.6 instead of 15.9 lanes are active per
+// instruction — but the bookkeeping around it (the vote and the walking flags of every phase, the buffer, the second
+// ray set-up and queue push of a resumed group) adds more warp-instructions than the loop saves: 176 M instead of 172 M
+// on bounce 1, 171 M instead of 153 M on the coherent camera rays, and the whole step is 7 % SLOWER (3 995 -> 3 720
+// Mpaths/s) whatever the threshold (5, 8, 12).  Off by default (RTB_EXTEND_EVICT=1 enables it); kept as the measured
+// answer to "raise the lanes per instruction of wf_extend": it can be done, and it does not pay.
+#ifndef RTB_EVICT_AT
+#define RTB_EVICT_AT 8
+#endif
+constexpr uint32_t kEvictAt = RTB_EVICT_AT;
+constexpr uint32_t kEvictFlushAt = 32u - kEvictAt;            // a buffer this full cannot take another eviction for sure
+constexpr uint32_t kEvictWarpBytes = 32u * 48u;               // {o, time} {d, bits(slot)} {node address, t, object, queue position}
+
+template <bool COUNT>
+__device__ __forceinline__ void extend_group(const WfParams& P, float4* __restrict__ pool, uint32_t& buffered, bool valid,
+                                             float3 o, float3 d, float time, uint32_t slot_bits, uint32_t at, uint32_t i,
+                                             float best_t, uint32_t best_node, bool may_evict, uint32_t& n_box,
+                                             uint32_t& n_obj) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const float t_min = 0.001f;
+    const PackedRay pr = packed_ray_setup(P.R.scene, o, d);
+    const __half2 ix = as_h2(pr.ix), iy = as_h2(pr.iy), iz = as_h2(pr.iz);
+    const __half2 nx = as_h2(pr.nx), ny = as_h2(pr.ny), nz = as_h2(pr.nz);
+    __half2 K = packed_interval(t_min, best_t, pr.sigma);
+    bool walking = valid, evicted = false;
+    for (;;) {
+        uint4 n = make_uint4(0u, 0u, 0u, RTB_META_END);
+        if (walking) {
+            for (;;) {  // to the next leaf, or to the end
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(n.x), "=r"(n.y), "=r"(n.z), "=r"(n.w) : "r"(i));
+                if (n.w >= (1u << 30)) break;
+                if (COUNT) ++n_box;
+                const __half2 tx = __hfma2(as_h2(n.x), ix, nx);
+                const __half2 ty = __hfma2(as_h2(n.y), iy, ny);
+                const __half2 tz = __hfma2(as_h2(n.z), iz, nz);
+                const __half2 r = __hmax2(__hmax2(tx, ty), __hmax2(tz, K));
+                const bool miss = __hge(__high2half(r), __hneg(__low2half(r)));
+                i = miss ? n.w : i + 16u;
+            }
+            if (n.w == RTB_META_END) walking = false;
+        }
+        const uint32_t alive = __ballot_sync(0xffffffffu, walking);
+        if (alive == 0u) break;
+        const uint32_t n_alive = __popc(alive);
+        if (may_evict && n_alive <= kEvictAt && buffered + n_alive <= 32u) {
+            if (walking) {
+                const uint32_t e = buffered + __popc(alive & ((1u << lane) - 1u));
+                pool[3u * e] = make_float4(o.x, o.y, o.z, time);
+                pool[3u * e + 1u] = make_float4(d.x, d.y, d.z, __uint_as_float(slot_bits));
+                pool[3u * e + 2u] = make_float4(__uint_as_float(i), best_t, __uint_as_float(best_node), __uint_as_float(at));
+                evicted = true;
+            }
+            buffered += n_alive;
+            break;
+        }
+        if (walking) {  // the leaf the lane stopped at: the reference's sphere test (src/objects.zig:116-149)
+            if (COUNT) ++n_obj;
+            uint4 m;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(i));
+            const float3 c1 = f3(__uint_as_float(n.x), __uint_as_float(n.y), __uint_as_float(n.z));
+            const float3 cv = f3(__uint_as_float(m.x), __uint_as_float(m.y), __uint_as_float(m.z));
+            const float3 center = ((n.w >> 30) == KIND_MOVING_SPHERE) ? c1 + splat3(time) * cv : c1;
+            float root;
+            if (sphere_root_a(o, d, length_squared(d), center, __uint_as_float(m.w), t_min, best_t, root)) {
+                best_t = root;
+                best_node = n.w & RTB_META_INDEX_MASK;
+                K = packed_interval(t_min, root, pr.sigma);
+            }
+            i += 32u;
+        }
+    }
+    __syncwarp();  // the buffer's entries are read by other lanes when the stragglers resume
+    const bool done = valid && !evicted;
+    uint32_t cls = CLASS_MISS;
+    if (done && best_node != 0xffffffffu) cls = P.R.scene.object_class[best_node];
+    const uint32_t j = queue_reserve(P.hit_count, done, cls);
+    if (done) P.hitq[(size_t)cls * P.capacity + j] = make_uint4(at, __float_as_uint(best_t), best_node, slot_bits);
+}
+
+// The stragglers in the warp's buffer, as one group that runs to the end.
+template <bool COUNT>
+__device__ __forceinline__ void extend_resume(const WfParams& P, float4* __restrict__ pool, uint32_t& buffered,
+                                              uint32_t& n_box, uint32_t& n_obj) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool valid = lane < buffered;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+    if (valid) {
+        a = pool[3u * lane];
+        b = pool[3u * lane + 1u];
+        c = pool[3u * lane + 2u];
+    }
+    __syncwarp();
+    uint32_t none = 32u;  // no room: this group never evicts
+    extend_group<COUNT>(P, pool, none, valid, f3(a), f3(b), a.w, __float_as_uint(b.w), __float_as_uint(c.w),
+                        __float_as_uint(c.x), c.y, __float_as_uint(c.z), false, n_box, n_obj);
+    buffered = 0u;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_extend_evict(const WfParams P) {
+    __shared__ ChunkMap map;
+    const TimelineScope tl(P);
+    chunk_map_init(map, P.count_in, kOctants, kExtendThreads);
+    if (blockIdx.x == 0 && threadIdx.x < kBins) {
+        P.count_out[threadIdx.x] = 0u;
+        P.hit_count_next[threadIdx.x] = 0u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.survivors && P.segment <= kSurvivorSlots) {
+        uint32_t total = 0;
+        for (uint32_t b = 0; b < kOctants; ++b) total += map.count[b];
+        P.survivors[P.segment - 1u] = total;
+    }
+    const uint32_t total_chunks = map.first_chunk[kBins];
+    const uint32_t oct_stride = P.R.scene.pk_slots;
+    const float4* __restrict__ layouts = reinterpret_cast<const float4*>(P.R.scene.pk_nodes);
+    float4* __restrict__ pool = rtb_smem_nodes + oct_stride + (threadIdx.x >> 5) * (kEvictWarpBytes / 16u);
+    uint32_t staged = kOctants, buffered = 0u;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(rtb_smem_nodes) + P.zero;
+    uint32_t n_box = 0, n_obj = 0, n_rays = 0;
+    const uint32_t per_cta = (total_chunks + gridDim.x - 1u) / gridDim.x;
+    const uint32_t c_end = (blockIdx.x + 1u) * per_cta < total_chunks ? (blockIdx.x + 1u) * per_cta : total_chunks;
+    for (uint32_t c = blockIdx.x * per_cta; c < c_end; ++c) {
+        uint32_t oct = 0;
+        while (c >= map.first_chunk[oct + 1u]) ++oct;
+        if (oct != staged) {
+            // the buffered stragglers hold addresses into the layout that is about to be replaced
+            if (buffered) extend_resume<COUNT>(P, pool, buffered, n_box, n_obj);
+            __syncthreads();
+            const float4* __restrict__ nodes = layouts + (size_t)oct * oct_stride;
+            for (uint32_t i = threadIdx.x; i < oct_stride; i += blockDim.x) {
+                float4 v = nodes[i];
+                const uint32_t meta = __float_as_uint(v.w);
+                if (meta < (1u << 30)) v.w = __uint_as_float(smem_base + meta * 16u);
+                rtb_smem_nodes[i] = v;
+            }
+            __syncthreads();
+            staged = oct;
+        }
+        const uint32_t i = (c - map.first_chunk[oct]) * kExtendThreads + threadIdx.x;
+        const bool valid = i < map.count[oct];
+        const size_t at = (size_t)oct * P.capacity + i;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (valid) {
+            a = P.in.rays[2u * at];
+            b = P.in.rays[2u * at + 1u];
+            if (COUNT) ++n_rays;
+        }
+        extend_group<COUNT>(P, pool, buffered, valid, f3(a), f3(b), a.w, __float_as_uint(b.w), (uint32_t)at, smem_base,
+                            __int_as_float(0x7f800000), 0xffffffffu, true, n_box, n_obj);
+        if (buffered >= kEvictFlushAt) extend_resume<COUNT>(P, pool, buffered, n_box, n_obj);
+    }
+    if (buffered) extend_resume<COUNT>(P, pool, buffered, n_box, n_obj);
+    if (COUNT) {
+        warp_add(&P.R.counters[0], n_rays);
+        warp_add(&P.R.counters[1], n_box);
+        warp_add(&P.R.counters[2], n_obj);
+    }
+    tl.finish(P, TL_EXTEND);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // wf_extend_stream — the extend kernel for INCOHERENT rays (bounces >= 1) over the packed SAH16 layout.
 //
 // ncu on the plain kernel (profiles/r2d_*): bounce rays keep 14 of 32 lanes busy.  The compiler turns its node loop
@@ -915,8 +1089,31 @@ static cudaError_t wf_launch_extend_stream(const WfParams& P, uint32_t grid, cud
     k<<<grid, kExtendThreads, smem, stream>>>(P);
     return cudaGetLastError();
 }
+// RTB_EXTEND_EVICT=1 renders SAH16 with wf_extend_evict (off by default: measured slower, see its header).
+static bool wf_evict_enabled() {
+    static const bool v = [] { const char* s = std::getenv("RTB_EXTEND_EVICT"); return s && s[0] == '1'; }();
+    return v;
+}
+static size_t wf_evict_smem_bytes(const DevScene& sc) {
+    return (size_t)sc.pk_slots * 16u + (kExtendThreads / 32u) * kEvictWarpBytes;
+}
+template <bool COUNT>
+static cudaError_t wf_launch_extend_evict(const WfParams& P, uint32_t grid, cudaStream_t stream) {
+    const size_t smem = wf_evict_smem_bytes(P.R.scene);
+    auto k = wf_extend_evict<COUNT>;
+    if (smem > 40u * 1024u) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, kExtendThreads, smem, stream>>>(P);
+    return cudaGetLastError();
+}
 template <bool COUNT, bool QUADS>
 static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
+    // three CTAs of the eviction kernel (layout + 24 KB of straggler buffers each) must still fit an SM
+    if (P.R.ordered == 3u && smem_nodes && !QUADS && wf_stream_mode() == 0 && wf_evict_enabled() &&
+        wf_evict_smem_bytes(P.R.scene) <= 72u * 1024u)
+        return wf_launch_extend_evict<COUNT>(P, grid, stream);
     if (P.R.ordered == 3u && smem_nodes && !QUADS && wf_stream_mode() >= (P.segment == 1u ? 2 : 1))
         return wf_launch_extend_stream<COUNT>(P, grid, stream);
     if (P.R.ordered == 3u) return wf_launch_extend_slab<COUNT, QUADS, kSlabPacked>(P, smem_nodes, grid, stream);
