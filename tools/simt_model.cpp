@@ -97,6 +97,20 @@ int main(int argc, char** argv) {
             }
         }
     }
+    if (scheme == 5) {
+        // trip-count utilisation (mean / max of the per-ray visit counts of a warp) if a visit covered k binary nodes:
+        // a wider node shortens every walk by the same factor and leaves the ratio where it is
+        double sum[3] = {0,0,0}, mx[3] = {0,0,0}; const int ks[3] = {1, 2, 4};
+        for (int oc=0;oc<8;++oc) for (size_t w=0; w+32<=q[oc].size(); w+=32) {
+            long m[3] = {0,0,0};
+            for (int t=0;t<32;++t){ Lane l; l.r=q[oc][w+t]; for(int k=0;k<3;++k) l.inv[k]=1.0f/l.r.d[k];
+                l.a=l.r.d[0]*l.r.d[0]+l.r.d[1]*l.r.d[1]+l.r.d[2]*l.r.d[2]; l.i=0; l.best=INFINITY; l.obj=-1; long v=0;
+                for(;;){ const Node& n=L[oc][l.i]; uint32_t mm=fb(n.f[3]); if (mm < (1u<<30)) { ++v; l.i = slab_miss(n,l,l.best)? mm : l.i+1; } else if (mm==0xffffffffu) break; else { sphere(l,n); ++v; l.i++; } }
+                for (int j=0;j<3;++j){ long u=(v+ks[j]-1)/ks[j]; sum[j]+=u; m[j]=std::max(m[j],u); } }
+            for (int j=0;j<3;++j) mx[j]+=m[j]; }
+        for (int j=0;j<3;++j) printf("%s k=%d: mean walk %.1f visits, longest in its warp %.1f, utilisation %.3f\n", rayfile, ks[j], sum[j]/ (mx[j]? 1:1) / (double)(rays.size()/32*32), mx[j]/(rays.size()/32), sum[j]/(32.0*mx[j]));
+        return 0;
+    }
     if (scheme == 4) {
         // while-while (K = 1) with STRAGGLER EVICTION: at a phase boundary (all lanes at a leaf or done) a warp with at
         // most T lanes still walking writes them to a continuation queue and ends; the stragglers of an octant are

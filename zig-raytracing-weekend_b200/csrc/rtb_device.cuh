@@ -200,10 +200,13 @@ __device__ __forceinline__ DRay get_ray(const DevCamera& cam, const RngKey& k) {
     float3 origin = cam.center;
     if (!(cam.defocus_angle <= 0.0f)) {
         float px_d, py_d;
-        for (uint32_t j = 0;; ++j) {
-            const float4 b = rng_block(k, 0u, 1u + (j >> 1));
-            px_d = range_pm1((j & 1u) ? b.z : b.x);
-            py_d = range_pm1((j & 1u) ? b.w : b.y);
+        for (uint32_t jb = 1u;; ++jb) {  // tries 2(jb - 1) and 2(jb - 1) + 1 share block jb: generated once
+            const float4 b = rng_block(k, 0u, jb);
+            px_d = range_pm1(b.x);
+            py_d = range_pm1(b.y);
+            if (px_d * px_d + py_d * py_d + 0.0f * 0.0f < 1.0f) break;
+            px_d = range_pm1(b.z);
+            py_d = range_pm1(b.w);
             if (px_d * px_d + py_d * py_d + 0.0f * 0.0f < 1.0f) break;
         }
         origin = cam.center + cam.ddu * splat3(px_d) + cam.ddv * splat3(py_d);
