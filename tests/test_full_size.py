@@ -111,7 +111,7 @@ def test_config4_million_spheres_hits_against_the_oracle(pkg, orc):
         hb2, ac = (oc @ dd) ** 2, (dd @ dd) * (oc @ oc - float(h.radius) ** 2)
         return abs(hb2 - ac) <= 16.0 * 2.0 ** -24 * (hb2 + abs(ac))
 
-    for trav in (2, 3):        # SAH16 renders as SAH here: 3 M nodes do not fit the packed shared-memory layout
+    for trav in (2, 3):        # SAH16: 3 M nodes do not fit shared memory, the packed layout is walked from global memory
         got = scene.trace_rays(rays, traversal=trav)
         same = got["object"] == cpu["object"]
         both = same & hit

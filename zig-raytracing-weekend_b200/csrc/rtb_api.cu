@@ -678,6 +678,14 @@ static void pack_layout(const std::vector<float4>& oct8, uint32_t n_entries, Pac
     }
 }
 
+// The packed SAH16 layout is also built for scenes whose layout does not fit shared memory; it is then walked from
+// global memory: half the bytes and one load instead of two per visit against +8 % visits (binary16 planes over the
+// whole scene's extent inflate small boxes) = +15 % on the 1 M-sphere scene (profiles/r3h_million_ab.log).
+// RTB_PACK_LARGE=0 switches it off (such a scene then renders SAH16 as SAH, as before r3h).
+static bool pack_large_scenes() {
+    static const bool v = [] { const char* e = std::getenv("RTB_PACK_LARGE"); return !(e && e[0] == '0'); }();
+    return v;
+}
 static int ensure_layouts(RtbScene* sc, uint32_t mode);
 
 static void scene_free(RtbScene* sc) {
@@ -912,11 +920,12 @@ static int ensure_layouts(RtbScene* sc, uint32_t mode) {
         for (int o = 0; o < 8; ++o) sah_emit(desc, sah, sc->host_quad_slot, o, oct.data() + (size_t)o * sah_stride);
         rc = upload(sc, oct, &sc->dev.oct_nodes[2]);
         sc->dev.oct_n_nodes[2] = n_sah;
-        // SAH16: the same layouts packed, when one octant fits in shared memory (else SAH16 renders as SAH)
-        if (rc == RTB_OK && n_sah > 0 && ((size_t)n_sah + 1) * 32u <= 2 * megakernel_max_smem_nodes_bytes()) {
+        // SAH16: the same layouts packed (walked from shared memory when one octant fits, else from global memory)
+        const bool pack_large = pack_large_scenes();
+        if (rc == RTB_OK && n_sah > 0 && (pack_large || ((size_t)n_sah + 1) * 32u <= 2 * megakernel_max_smem_nodes_bytes())) {
             PackedLayout packed;
             pack_layout(oct, n_sah, packed);
-            if ((size_t)packed.n_slots * 16u <= megakernel_max_smem_nodes_bytes()) {
+            if (pack_large || (size_t)packed.n_slots * 16u <= megakernel_max_smem_nodes_bytes()) {
                 rc = upload(sc, packed.slots, &sc->dev.pk_nodes);
                 sc->dev.pk_slots = packed.n_slots;
                 for (int a = 0; a < 3; ++a) {
@@ -988,14 +997,14 @@ extern "C" int rtb_debug_packed_layout(const RtbSceneDesc* desc, uint32_t octant
     rc = sah_tree_build(desc, size, sah);
     if (rc != RTB_OK) return rc;
     const uint32_t n = sah.layout_nodes;
-    if (n == 0 || ((size_t)n + 1) * 32u > 2 * megakernel_max_smem_nodes_bytes())
+    if (n == 0 || (!pack_large_scenes() && ((size_t)n + 1) * 32u > 2 * megakernel_max_smem_nodes_bytes()))
         return fail(RTB_ERR_UNSUPPORTED, "scene too large for the packed layout");
     const size_t stride = 2 * ((size_t)n + 1);
     std::vector<float4> oct8(8 * stride, mkf4(0.0f, 0.0f, 0.0f, bits(RTB_META_END)));
     for (int oct = 0; oct < 8; ++oct) sah_emit(desc, sah, quad_slot, oct, oct8.data() + (size_t)oct * stride);
     PackedLayout packed;
     pack_layout(oct8, n, packed);
-    if ((size_t)packed.n_slots * 16u > megakernel_max_smem_nodes_bytes())
+    if (!pack_large_scenes() && (size_t)packed.n_slots * 16u > megakernel_max_smem_nodes_bytes())
         return fail(RTB_ERR_UNSUPPORTED, "scene too large for the packed layout");
     *n_slots_out = packed.n_slots;
     for (int a = 0; a < 3; ++a) {

@@ -93,7 +93,8 @@ struct DevScene {
     //                       {.., kind|object} {bits(subtype), 0, 0, 0x80000000 | quad slot}) — the last word of a leaf
     //                       always has bit 31 set, so "word 3 < 2^30" identifies exactly the box nodes' skip links;
     //   end sentinel (1 slot) word 3 = RTB_META_END.
-    // NULL when the packed layout would not fit in shared memory (then SAH16 renders as SAH).
+    // Walked from shared memory when one octant fits, else from global memory; NULL only with RTB_PACK_LARGE=0 for a
+    // scene that does not fit (then SAH16 renders as SAH).
     const uint4* pk_nodes;
     uint32_t pk_slots;  // slots per octant, sentinel included
     float pk_center[3], pk_inv_scale[3], pk_scale[3];

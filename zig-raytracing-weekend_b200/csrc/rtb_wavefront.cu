@@ -56,9 +56,10 @@ constexpr uint32_t kExtendThreads = RTB_EXTEND_THREADS;
 #define RTB_EXTEND_GRID_PER_SM 1
 #endif
 // The same for layouts that stay in global memory (the 1 M-sphere scene: an L2-latency-bound walk that wants every
-// warp it can get).
+// warp it can get: 32 registers and four 512-thread CTAs per SM instead of 40 and three measured +15 %,
+// profiles/r3i_million_ab.log).
 #ifndef RTB_EXTEND_GRID_PER_SM_GLOBAL
-#define RTB_EXTEND_GRID_PER_SM_GLOBAL 3
+#define RTB_EXTEND_GRID_PER_SM_GLOBAL 4
 #endif
 #ifndef RTB_SHADE_GRID_PER_SM
 #define RTB_SHADE_GRID_PER_SM 5
@@ -276,7 +277,11 @@ __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
 // RTB_TRAVERSAL_SAH16 (traverse_packed).
 enum : int { kSlabExact = 0, kSlabFma = 1, kSlabPacked = 2 };
 template <bool SMEM_NODES, bool COUNT, bool QUADS, int SLAB>
-__global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_extend(const WfParams P) {
+#ifndef RTB_EXTEND_MINBLOCKS_GLOBAL
+#define RTB_EXTEND_MINBLOCKS_GLOBAL 4
+#endif
+__global__ void __launch_bounds__(kExtendThreads, SMEM_NODES ? RTB_EXTEND_MINBLOCKS : RTB_EXTEND_MINBLOCKS_GLOBAL)
+wf_extend(const WfParams P) {
     __shared__ ChunkMap map;
     const TimelineScope tl(P);
     constexpr bool PACKED = SLAB == kSlabPacked;
@@ -302,15 +307,19 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
     uint32_t staged = kOctants;  // octant whose layout is in shared memory
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(rtb_smem_nodes) + P.zero;
     uint32_t n_box = 0, n_obj = 0, n_rays = 0;
-#if RTB_EXTEND_CONTIGUOUS
     // A CTA walks a CONTIGUOUS range of chunks: the chunks are ordered by octant, so it stages one or two layouts per
-    // launch instead of all eight (a strided walk meets every octant).
-    const uint32_t per_cta = (total_chunks + gridDim.x - 1u) / gridDim.x;
-    const uint32_t c_end = (blockIdx.x + 1u) * per_cta < total_chunks ? (blockIdx.x + 1u) * per_cta : total_chunks;
-    for (uint32_t c = blockIdx.x * per_cta; c < c_end; ++c) {
-#else
-    for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+    // launch instead of all eight (a strided walk meets every octant).  Layouts that stay in global memory
+    // (RTB_EXTEND_STRIDED_GLOBAL) are walked strided instead: then all CTAs are in the same one or two octants at any
+    // time, and those layouts — not all eight — are what the L2 has to hold.
+#ifndef RTB_EXTEND_STRIDED_GLOBAL
+#define RTB_EXTEND_STRIDED_GLOBAL 1
 #endif
+    constexpr bool STRIDED = !SMEM_NODES && RTB_EXTEND_STRIDED_GLOBAL;
+    const uint32_t per_cta = (total_chunks + gridDim.x - 1u) / gridDim.x;
+    const uint32_t c_last = (blockIdx.x + 1u) * per_cta < total_chunks ? (blockIdx.x + 1u) * per_cta : total_chunks;
+    const uint32_t c_end = STRIDED ? total_chunks : c_last;
+    const uint32_t c_step = STRIDED ? gridDim.x : 1u;
+    for (uint32_t c = STRIDED ? blockIdx.x : blockIdx.x * per_cta; c < c_end; c += c_step) {
         uint32_t oct = 0;
         while (c >= map.first_chunk[oct + 1u]) ++oct;
         const float4* __restrict__ nodes = layouts + (size_t)oct * oct_stride;
