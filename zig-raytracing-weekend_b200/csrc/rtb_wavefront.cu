@@ -415,23 +415,29 @@ constexpr uint32_t kEvictAt = RTB_EVICT_AT;
 constexpr uint32_t kEvictFlushAt = 32u - kEvictAt;            // a buffer this full cannot take another eviction for sure
 constexpr uint32_t kEvictWarpBytes = 32u * 48u;               // {o, time} {d, bits(slot)} {node address, t, object, queue position}
 
-template <bool COUNT>
-__device__ __forceinline__ void extend_group(const WfParams& P, float4* __restrict__ pool, uint32_t& buffered, bool valid,
-                                             float3 o, float3 d, float time, uint32_t slot_bits, uint32_t at, uint32_t i,
-                                             float best_t, uint32_t best_node, bool may_evict, uint32_t& n_box,
-                                             uint32_t& n_obj) {
+template <bool COUNT, bool SMEM>
+__device__ __forceinline__ void extend_group(const WfParams& P, const uint4* __restrict__ slots, float4* __restrict__ pool,
+                                             uint32_t& buffered, bool valid, float3 o, float3 d, float time,
+                                             uint32_t slot_bits, uint32_t at, uint32_t i, float best_t, uint32_t best_node,
+                                             bool may_evict, uint32_t& n_box, uint32_t& n_obj) {
     const uint32_t lane = threadIdx.x & 31u;
     const float t_min = 0.001f;
+    constexpr uint32_t kStep = SMEM ? 16u : 1u;  // SMEM: `i` is a shared-window address, else a slot index
     const PackedRay pr = packed_ray_setup(P.R.scene, o, d);
     const __half2 ix = as_h2(pr.ix), iy = as_h2(pr.iy), iz = as_h2(pr.iz);
     const __half2 nx = as_h2(pr.nx), ny = as_h2(pr.ny), nz = as_h2(pr.nz);
     __half2 K = packed_interval(t_min, best_t, pr.sigma);
     bool walking = valid, evicted = false;
+    const uint32_t n_start = __popc(__ballot_sync(0xffffffffu, valid));
     for (;;) {
         uint4 n = make_uint4(0u, 0u, 0u, RTB_META_END);
         if (walking) {
             for (;;) {  // to the next leaf, or to the end
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(n.x), "=r"(n.y), "=r"(n.z), "=r"(n.w) : "r"(i));
+                if (SMEM) {
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(n.x), "=r"(n.y), "=r"(n.z), "=r"(n.w) : "r"(i));
+                } else {
+                    n = slots[i];
+                }
                 if (n.w >= (1u << 30)) break;
                 if (COUNT) ++n_box;
                 const __half2 tx = __hfma2(as_h2(n.x), ix, nx);
@@ -439,14 +445,15 @@ __device__ __forceinline__ void extend_group(const WfParams& P, float4* __restri
                 const __half2 tz = __hfma2(as_h2(n.z), iz, nz);
                 const __half2 r = __hmax2(__hmax2(tx, ty), __hmax2(tz, K));
                 const bool miss = __hge(__high2half(r), __hneg(__low2half(r)));
-                i = miss ? n.w : i + 16u;
+                i = miss ? n.w : i + kStep;
             }
             if (n.w == RTB_META_END) walking = false;
         }
         const uint32_t alive = __ballot_sync(0xffffffffu, walking);
         if (alive == 0u) break;
         const uint32_t n_alive = __popc(alive);
-        if (may_evict && n_alive <= kEvictAt && buffered + n_alive <= 32u) {
+        // (a group that has lost no lane yet is not evicted: every eviction must come with progress)
+        if (may_evict && n_alive <= kEvictAt && n_alive < n_start && buffered + n_alive <= 32u) {
             if (walking) {
                 const uint32_t e = buffered + __popc(alive & ((1u << lane) - 1u));
                 pool[3u * e] = make_float4(o.x, o.y, o.z, time);
@@ -460,7 +467,11 @@ __device__ __forceinline__ void extend_group(const WfParams& P, float4* __restri
         if (walking) {  // the leaf the lane stopped at: the reference's sphere test (src/objects.zig:116-149)
             if (COUNT) ++n_obj;
             uint4 m;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(i));
+            if (SMEM) {
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(i));
+            } else {
+                m = slots[i + 1u];
+            }
             const float3 c1 = f3(__uint_as_float(n.x), __uint_as_float(n.y), __uint_as_float(n.z));
             const float3 cv = f3(__uint_as_float(m.x), __uint_as_float(m.y), __uint_as_float(m.z));
             const float3 center = ((n.w >> 30) == KIND_MOVING_SPHERE) ? c1 + splat3(time) * cv : c1;
@@ -470,7 +481,7 @@ __device__ __forceinline__ void extend_group(const WfParams& P, float4* __restri
                 best_node = n.w & RTB_META_INDEX_MASK;
                 K = packed_interval(t_min, root, pr.sigma);
             }
-            i += 32u;
+            i += 2u * kStep;
         }
     }
     __syncwarp();  // the buffer's entries are read by other lanes when the stragglers resume
@@ -481,10 +492,11 @@ __device__ __forceinline__ void extend_group(const WfParams& P, float4* __restri
     if (done) P.hitq[(size_t)cls * P.capacity + j] = make_uint4(at, __float_as_uint(best_t), best_node, slot_bits);
 }
 
-// The stragglers in the warp's buffer, as one group that runs to the end.
-template <bool COUNT>
-__device__ __forceinline__ void extend_resume(const WfParams& P, float4* __restrict__ pool, uint32_t& buffered,
-                                              uint32_t& n_box, uint32_t& n_obj) {
+// The stragglers in the warp's buffer as one dense group.  `again`: its own last few walkers may be evicted once more
+// (they then wait for the next group); otherwise it runs to the end (before the layout changes, and at the very end).
+template <bool COUNT, bool SMEM>
+__device__ __forceinline__ void extend_resume(const WfParams& P, const uint4* __restrict__ slots, float4* __restrict__ pool,
+                                              uint32_t& buffered, bool again, uint32_t& n_box, uint32_t& n_obj) {
     const uint32_t lane = threadIdx.x & 31u;
     const bool valid = lane < buffered;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
@@ -494,14 +506,17 @@ __device__ __forceinline__ void extend_resume(const WfParams& P, float4* __restr
         c = pool[3u * lane + 2u];
     }
     __syncwarp();
-    uint32_t none = 32u;  // no room: this group never evicts
-    extend_group<COUNT>(P, pool, none, valid, f3(a), f3(b), a.w, __float_as_uint(b.w), __float_as_uint(c.w),
-                        __float_as_uint(c.x), c.y, __float_as_uint(c.z), false, n_box, n_obj);
     buffered = 0u;
+    extend_group<COUNT, SMEM>(P, slots, pool, buffered, valid, f3(a), f3(b), a.w, __float_as_uint(b.w), __float_as_uint(c.w),
+                              __float_as_uint(c.x), c.y, __float_as_uint(c.z), again, n_box, n_obj);
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_extend_evict(const WfParams P) {
+#ifndef RTB_EVICT_AGAIN
+#define RTB_EVICT_AGAIN 1
+#endif
+template <bool COUNT, bool SMEM>
+__global__ void __launch_bounds__(kExtendThreads, SMEM ? RTB_EXTEND_MINBLOCKS : RTB_EXTEND_MINBLOCKS_GLOBAL)
+wf_extend_evict(const WfParams P) {
     __shared__ ChunkMap map;
     const TimelineScope tl(P);
     chunk_map_init(map, P.count_in, kOctants, kExtendThreads);
@@ -517,28 +532,37 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
     const uint32_t total_chunks = map.first_chunk[kBins];
     const uint32_t oct_stride = P.R.scene.pk_slots;
     const float4* __restrict__ layouts = reinterpret_cast<const float4*>(P.R.scene.pk_nodes);
-    float4* __restrict__ pool = rtb_smem_nodes + oct_stride + (threadIdx.x >> 5) * (kEvictWarpBytes / 16u);
-    uint32_t staged = kOctants, buffered = 0u;
+    // dynamic shared memory: [the staged layout (SMEM only)] [one 32-entry straggler buffer per warp]
+    float4* __restrict__ pool = rtb_smem_nodes + (SMEM ? oct_stride : 0u) + (threadIdx.x >> 5) * (kEvictWarpBytes / 16u);
+    uint32_t current = kOctants, buffered = 0u;  // octant of the layout the buffered stragglers (and the staged copy) belong to
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(rtb_smem_nodes) + P.zero;
+    const uint4* __restrict__ slots = nullptr;
     uint32_t n_box = 0, n_obj = 0, n_rays = 0;
+    // SMEM: a contiguous range of chunks per CTA (one or two layouts to stage); global layouts: strided, so that all CTAs
+    // are in the same one or two octants at any time (see wf_extend)
     const uint32_t per_cta = (total_chunks + gridDim.x - 1u) / gridDim.x;
-    const uint32_t c_end = (blockIdx.x + 1u) * per_cta < total_chunks ? (blockIdx.x + 1u) * per_cta : total_chunks;
-    for (uint32_t c = blockIdx.x * per_cta; c < c_end; ++c) {
+    const uint32_t c_last = (blockIdx.x + 1u) * per_cta < total_chunks ? (blockIdx.x + 1u) * per_cta : total_chunks;
+    const uint32_t c_end = SMEM ? c_last : total_chunks;
+    const uint32_t c_step = SMEM ? 1u : gridDim.x;
+    for (uint32_t c = SMEM ? blockIdx.x * per_cta : blockIdx.x; c < c_end; c += c_step) {
         uint32_t oct = 0;
         while (c >= map.first_chunk[oct + 1u]) ++oct;
-        if (oct != staged) {
-            // the buffered stragglers hold addresses into the layout that is about to be replaced
-            if (buffered) extend_resume<COUNT>(P, pool, buffered, n_box, n_obj);
-            __syncthreads();
-            const float4* __restrict__ nodes = layouts + (size_t)oct * oct_stride;
-            for (uint32_t i = threadIdx.x; i < oct_stride; i += blockDim.x) {
-                float4 v = nodes[i];
-                const uint32_t meta = __float_as_uint(v.w);
-                if (meta < (1u << 30)) v.w = __uint_as_float(smem_base + meta * 16u);
-                rtb_smem_nodes[i] = v;
+        if (oct != current) {
+            // the buffered stragglers hold positions in the layout that is about to be left
+            if (buffered) extend_resume<COUNT, SMEM>(P, slots, pool, buffered, false, n_box, n_obj);
+            slots = reinterpret_cast<const uint4*>(layouts + (size_t)oct * oct_stride);
+            if (SMEM) {
+                __syncthreads();
+                const float4* __restrict__ nodes = layouts + (size_t)oct * oct_stride;
+                for (uint32_t i = threadIdx.x; i < oct_stride; i += blockDim.x) {
+                    float4 v = nodes[i];
+                    const uint32_t meta = __float_as_uint(v.w);
+                    if (meta < (1u << 30)) v.w = __uint_as_float(smem_base + meta * 16u);
+                    rtb_smem_nodes[i] = v;
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            staged = oct;
+            current = oct;
         }
         const uint32_t i = (c - map.first_chunk[oct]) * kExtendThreads + threadIdx.x;
         const bool valid = i < map.count[oct];
@@ -549,11 +573,11 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
             b = P.in.rays[2u * at + 1u];
             if (COUNT) ++n_rays;
         }
-        extend_group<COUNT>(P, pool, buffered, valid, f3(a), f3(b), a.w, __float_as_uint(b.w), (uint32_t)at, smem_base,
-                            __int_as_float(0x7f800000), 0xffffffffu, true, n_box, n_obj);
-        if (buffered >= kEvictFlushAt) extend_resume<COUNT>(P, pool, buffered, n_box, n_obj);
+        extend_group<COUNT, SMEM>(P, slots, pool, buffered, valid, f3(a), f3(b), a.w, __float_as_uint(b.w), (uint32_t)at,
+                                  SMEM ? smem_base : 0u, __int_as_float(0x7f800000), 0xffffffffu, true, n_box, n_obj);
+        if (buffered >= kEvictFlushAt) extend_resume<COUNT, SMEM>(P, slots, pool, buffered, RTB_EVICT_AGAIN != 0, n_box, n_obj);
     }
-    if (buffered) extend_resume<COUNT>(P, pool, buffered, n_box, n_obj);
+    if (buffered) extend_resume<COUNT, SMEM>(P, slots, pool, buffered, false, n_box, n_obj);
     if (COUNT) {
         warp_add(&P.R.counters[0], n_rays);
         warp_add(&P.R.counters[1], n_box);
@@ -1098,18 +1122,21 @@ static cudaError_t wf_launch_extend_stream(const WfParams& P, uint32_t grid, cud
     k<<<grid, kExtendThreads, smem, stream>>>(P);
     return cudaGetLastError();
 }
-// RTB_EXTEND_EVICT=1 renders SAH16 with wf_extend_evict (off by default: measured slower, see its header).
-static bool wf_evict_enabled() {
-    static const bool v = [] { const char* s = std::getenv("RTB_EXTEND_EVICT"); return s && s[0] == '1'; }();
+// RTB_EXTEND_EVICT=1 renders SAH16 scenes (spheres only) with wf_extend_evict — over the staged layout, or over the global
+// one for large scenes.  Off by default: measured slower in both (see the kernel's header; the 1 M-sphere scene, whose
+// walk is bound by L2 latency at 5.6 lanes per instruction: 290 -> 275 Mpaths/s for thresholds 4 ... 20,
+// profiles/r3k_million_evict_ab.log).
+static int wf_evict_mode() {
+    static const int v = [] { const char* s = std::getenv("RTB_EXTEND_EVICT"); return s && s[0] ? std::atoi(s) : -1; }();
     return v;
 }
-static size_t wf_evict_smem_bytes(const DevScene& sc) {
-    return (size_t)sc.pk_slots * 16u + (kExtendThreads / 32u) * kEvictWarpBytes;
+static size_t wf_evict_smem_bytes(const DevScene& sc, bool smem_nodes) {
+    return (smem_nodes ? (size_t)sc.pk_slots * 16u : 0u) + (kExtendThreads / 32u) * kEvictWarpBytes;
 }
-template <bool COUNT>
+template <bool COUNT, bool SMEM>
 static cudaError_t wf_launch_extend_evict(const WfParams& P, uint32_t grid, cudaStream_t stream) {
-    const size_t smem = wf_evict_smem_bytes(P.R.scene);
-    auto k = wf_extend_evict<COUNT>;
+    const size_t smem = wf_evict_smem_bytes(P.R.scene, SMEM);
+    auto k = wf_extend_evict<COUNT, SMEM>;
     if (smem > 40u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1119,10 +1146,13 @@ static cudaError_t wf_launch_extend_evict(const WfParams& P, uint32_t grid, cuda
 }
 template <bool COUNT, bool QUADS>
 static cudaError_t wf_launch_extend(const WfParams& P, bool smem_nodes, uint32_t grid, cudaStream_t stream) {
-    // three CTAs of the eviction kernel (layout + 24 KB of straggler buffers each) must still fit an SM
-    if (P.R.ordered == 3u && smem_nodes && !QUADS && wf_stream_mode() == 0 && wf_evict_enabled() &&
-        wf_evict_smem_bytes(P.R.scene) <= 72u * 1024u)
-        return wf_launch_extend_evict<COUNT>(P, grid, stream);
+    if (P.R.ordered == 3u && !QUADS && wf_stream_mode() == 0) {
+        const int mode = wf_evict_mode();
+        // three CTAs of the shared-memory variant (layout + 24 KB of straggler buffers each) must still fit an SM
+        if (smem_nodes && mode == 1 && wf_evict_smem_bytes(P.R.scene, true) <= 72u * 1024u)
+            return wf_launch_extend_evict<COUNT, true>(P, grid, stream);
+        if (!smem_nodes && mode == 1) return wf_launch_extend_evict<COUNT, false>(P, grid, stream);
+    }
     if (P.R.ordered == 3u && smem_nodes && !QUADS && wf_stream_mode() >= (P.segment == 1u ? 2 : 1))
         return wf_launch_extend_stream<COUNT>(P, grid, stream);
     if (P.R.ordered == 3u) return wf_launch_extend_slab<COUNT, QUADS, kSlabPacked>(P, smem_nodes, grid, stream);
