@@ -17,7 +17,7 @@ for world, camo in worlds:
     rays = np.zeros(3000, dtype=np.dtype(p._ffi.RAY_DTYPE))
     rays["origin"] = rng.uniform(-10, 10, (3000, 3)); rays["direction"] = rng.normal(size=(3000, 3))
     rays["t_min"] = 0.001; rays["t_max"] = np.inf; rays["time"] = rng.random(3000)
-    for trav in (0, 1, 2):
+    for trav in (0, 1, 2, 3):
         scene.trace_rays(rays, traversal=trav)
         for integ in (0, 1):
             scene.render(cam, p.render_options(seed=3, integrator=integ, traversal=trav, flags=p.RTB_FLAG_COUNT_WORK))

@@ -181,6 +181,66 @@ __device__ __forceinline__ float3 random_unit_vector(const RngKey& k, uint32_t s
     }
 }
 
+// vec3.randomUnitVector for a whole warp at once — the same value for every lane as random_unit_vector, in fewer
+// rounds.  The rejection loop accepts with probability pi/6, so the slowest of 32 lanes needs ~5.5 tries while a lane
+// needs 1.9 on average, and in the plain loop the lanes that are done idle through those rounds.  Try j of a path is a
+// pure function of (seed; pixel, sample, segment, block j), so ANY lane can evaluate it: after the first round the
+// lanes are redistributed over the paths still pending — c = 32 / pending (rounded down to a power of two) lanes per
+// path evaluate its next c tries side by side, and the path takes the accepted one with the lowest index (the one the
+// sequential loop would have stopped at).  Expected rounds per warp: ~3.2 instead of ~5.5.
+// Must be called by all 32 lanes (`need` = this lane has a path); `scratch` = 32 uint4 of shared memory owned by the warp.
+__device__ __forceinline__ float3 random_unit_vector_coop(bool need, const RngKey& key, uint32_t segment, uint4* scratch) {
+    const uint32_t lane = threadIdx.x & 31u;
+    float3 p = f3(1.0f, 0.0f, 0.0f);
+    bool pending = need;
+    if (need) {
+        const float4 b = rng_block(key, segment, 0u);
+        p = f3(range_pm1(b.x), range_pm1(b.y), range_pm1(b.z));
+        pending = !(length_squared(p) < 1.0f);
+    }
+    uint32_t next_try = 1u;
+    for (;;) {
+        const uint32_t pend = __ballot_sync(0xffffffffu, pending);
+        if (pend == 0u) break;
+        const uint32_t n_p = __popc(pend);
+        const uint32_t lg = (uint32_t)__clz((int)(n_p - 1u)) - 27u;  // log2 of the lanes per pending path: 5 .. 0
+        const uint32_t rank = __popc(pend & ((1u << lane) - 1u));    // of this lane's own path among the pending ones
+        if (pending) scratch[rank] = make_uint4(key.pixel, key.sample, next_try, 0u);
+        __syncwarp();
+        const uint32_t k = lane >> lg, off = lane & ((1u << lg) - 1u);  // this lane evaluates try `off` of pending path k
+        float3 q = f3(0.0f, 0.0f, 0.0f);
+        bool ok = false;
+        if (k < n_p) {
+            const uint4 w = scratch[k];
+            RngKey kk;
+            kk.seed = key.seed;
+            kk.pixel = w.x;
+            kk.sample = w.y;
+            const float4 b = rng_block(kk, segment, w.z + off);
+            q = f3(range_pm1(b.x), range_pm1(b.y), range_pm1(b.z));
+            ok = length_squared(q) < 1.0f;
+        }
+        const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+        // the lanes that worked for this lane's path: [rank << lg, (rank + 1) << lg)
+        const uint32_t group = (lg == 5u ? 0xffffffffu : ((1u << (1u << lg)) - 1u) << (rank << lg));
+        const uint32_t won = pending ? (okm & group) : 0u;
+        const uint32_t from = won ? (uint32_t)__ffs((int)won) - 1u : lane;
+        const float qx = __shfl_sync(0xffffffffu, q.x, from);
+        const float qy = __shfl_sync(0xffffffffu, q.y, from);
+        const float qz = __shfl_sync(0xffffffffu, q.z, from);
+        if (pending) {
+            if (won) {
+                p = f3(qx, qy, qz);
+                pending = false;
+            } else {
+                next_try += 1u << lg;
+            }
+        }
+        __syncwarp();  // scratch is rewritten in the next round
+    }
+    return unit_vector(p);
+}
+
 // ------------------------------------------------------------------ rays
 struct DRay {
     float3 o, d;
@@ -1100,14 +1160,15 @@ struct ShadeResult {
 };
 
 __device__ __forceinline__ ShadeResult shade_hit(const DevScene& sc, const DHit& h, float4 m0, float4 m1, const DRay& r,
-                                                 const RngKey& key, uint32_t segment);
+                                                 const RngKey& key, uint32_t segment, const float3* unit = nullptr);
 
 // emitted + scatter for the nearest hit (src/camera.zig:194-196 -> src/material.zig:18-30).
 // `segment` (>= 1) keys this hit's RNG stream; block 0 word 3 is the dielectric reflectance draw.
 // `f0,f1` = the hit object's leaf record, `m0,m1` = its material record.
 template <bool QUADS>
 __device__ __forceinline__ ShadeResult shade_rec(const DevScene& sc, float4 f0, float4 f1, float4 m0, float4 m1,
-                                                 const DRay& r, float t, const RngKey& key, uint32_t segment) {
+                                                 const DRay& r, float t, const RngKey& key, uint32_t segment,
+                                                 const float3* unit = nullptr) {
     const uint32_t tex_type = (__float_as_uint(m0.x) >> 8) & 0xffu;
     DHit h;
     if (QUADS && (__float_as_uint(f0.w) >> 30) == KIND_QUAD && __float_as_uint(f1.x) == COMPLEX_GENERIC) {
@@ -1122,12 +1183,13 @@ __device__ __forceinline__ ShadeResult shade_rec(const DevScene& sc, float4 f0, 
         h = finish_hit_rec<QUADS, true>(f0, f1, complex_tables(sc), r, t);
     else
         h = finish_hit_rec<QUADS, false>(f0, f1, complex_tables(sc), r, t);
-    return shade_hit(sc, h, m0, m1, r, key, segment);
+    return shade_hit(sc, h, m0, m1, r, key, segment, unit);
 }
 
-// emitted + scatter once the hit record and the material record are known.
+// emitted + scatter once the hit record and the material record are known.  `unit` (optional): this hit's
+// randomUnitVector, already drawn by random_unit_vector_coop (lambertian and metal only).
 __device__ __forceinline__ ShadeResult shade_hit(const DevScene& sc, const DHit& h, float4 m0, float4 m1, const DRay& r,
-                                                 const RngKey& key, uint32_t segment) {
+                                                 const RngKey& key, uint32_t segment, const float3* unit) {
     ShadeResult out;
     const TexTables tt{sc.textures, sc.perlins, sc.images};
     out.emitted = f3(0.0f, 0.0f, 0.0f);
@@ -1137,8 +1199,7 @@ __device__ __forceinline__ ShadeResult shade_hit(const DevScene& sc, const DHit&
     out.scattered.o = h.p;
     out.scattered.time = r.time;
     if (type == RTB_MAT_LAMBERTIAN) {  // src/material.zig:43-54
-        const float4 b0 = rng_block(key, segment, 0u);
-        float3 dir = h.normal + random_unit_vector(key, segment, b0);
+        float3 dir = h.normal + (unit ? *unit : random_unit_vector(key, segment, rng_block(key, segment, 0u)));
         const float s = 1e-8f;
         if (fabsf(dir.x) < s && fabsf(dir.y) < s && fabsf(dir.z) < s) dir = h.normal;  // nearZero
         out.scattered.d = dir;
@@ -1146,9 +1207,9 @@ __device__ __forceinline__ ShadeResult shade_hit(const DevScene& sc, const DHit&
             (tex_type == RTB_TEX_SOLID) ? f3(m1) : texture_value_slow(tt, __float_as_uint(m0.y), h.u, h.v, h.p);
         out.scatters = true;
     } else if (type == RTB_MAT_METAL) {  // src/material.zig:65-70
-        const float4 b0 = rng_block(key, segment, 0u);
         const float3 reflected = reflect3(unit_vector(r.d), h.normal);
-        out.scattered.d = reflected + splat3(m0.z) * random_unit_vector(key, segment, b0);
+        out.scattered.d =
+            reflected + splat3(m0.z) * (unit ? *unit : random_unit_vector(key, segment, rng_block(key, segment, 0u)));
         out.attenuation = f3(m1);
         out.scatters = dot3(out.scattered.d, h.normal) > 0.0f;
     } else if (type == RTB_MAT_DIELECTRIC) {  // src/material.zig:80-98

@@ -73,6 +73,14 @@ constexpr uint32_t kExtendThreads = RTB_EXTEND_THREADS;
 #ifndef RTB_EXTEND_CONTIGUOUS
 #define RTB_EXTEND_CONTIGUOUS 1
 #endif
+// RTB_SHADE_COOP=1: wf_shade draws the random unit vectors of a lambertian / metal chunk warp-cooperatively
+// (random_unit_vector_coop: idle lanes evaluate the next tries of the paths whose rejection loop is still running).
+// Bit-identical; measured (profiles/r3m_coop_ab.log, r3n_coop_*.csv): 29 instead of 21-24 of 32 lanes per instruction
+// in wf_shade, but 95.5 M instead of 88.9 M warp-instructions on bounce 0 (the votes, the scratch exchange and the
+// shuffles of a round cost more than the rounds saved) and the step is flat (-0.5 %).  Off by default.
+#ifndef RTB_SHADE_COOP
+#define RTB_SHADE_COOP 0
+#endif
 #ifndef RTB_SHADE_MINBLOCKS
 #define RTB_SHADE_MINBLOCKS 3
 #endif
@@ -854,6 +862,7 @@ __global__ void __launch_bounds__(kExtendThreads, RTB_EXTEND_MINBLOCKS) wf_exten
 template <bool COUNT, bool QUADS>
 __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfParams P) {
     __shared__ ChunkMap map;
+    __shared__ uint4 coop_scratch[8][32];  // random_unit_vector_coop: one row per warp
     const TimelineScope tl(P);
     chunk_map_init(map, P.hit_count, kShadeClasses);
     const uint32_t total_chunks = map.first_chunk[kBins];
@@ -881,17 +890,30 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
         next.o = next.d = f3(0.f, 0.f, 0.f);
         next.time = 0.f;
         uint32_t slot = 0;
-        if (i < map.count[cls]) {
-            const uint4 e = P.hitq[(size_t)cls * P.capacity + i];
-            const float4 a = P.in.rays[2u * (size_t)e.x];
-            const float4 b = P.in.rays[2u * (size_t)e.x + 1u];
+        const bool valid = i < map.count[cls];
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, tl0 = a, tl1 = a;
+        if (valid) {
+            e = P.hitq[(size_t)cls * P.capacity + i];
+            a = P.in.rays[2u * (size_t)e.x];
+            b = P.in.rays[2u * (size_t)e.x + 1u];
+            slot = e.w;  // == bits(b.w); carried in the hit record so that the (T, L) gather does not wait for the ray
+            tl0 = P.TL[2u * (size_t)slot];
+            tl1 = P.TL[2u * (size_t)slot + 1u];
+        }
+        RngKey key;
+        key.seed = P.R.seed;
+        key.pixel = __float_as_uint(tl1.z);
+        key.sample = __float_as_uint(tl1.w);
+        // a chunk of solid-lambertian or metal hits: every lane needs a randomUnitVector; the warp draws them together
+        float3 unit = f3(0.f, 0.f, 0.f);
+        const bool coop = RTB_SHADE_COOP && (cls == CLASS_LAMBERT_SOLID || cls == CLASS_METAL);  // block-uniform
+        if (coop) unit = random_unit_vector_coop(valid, key, P.segment, coop_scratch[threadIdx.x >> 5]);
+        if (valid) {
             DRay r;
             r.o = f3(a);
             r.time = a.w;
             r.d = f3(b);
-            slot = e.w;  // == bits(b.w); carried in the hit record so that the (T, L) gather does not wait for the ray
-            const float4 tl0 = P.TL[2u * (size_t)slot];
-            const float4 tl1 = P.TL[2u * (size_t)slot + 1u];
             float3 T = f3(tl0);
             float3 L = f3(tl0.w, tl1.x, tl1.y);
             if (cls == CLASS_MISS) {  // block-uniform
@@ -900,11 +922,8 @@ __global__ void __launch_bounds__(256, RTB_SHADE_MINBLOCKS) wf_shade(const WfPar
                 if (COUNT) ++n_hits;
                 const float4* __restrict__ pr = P.R.scene.prims + 4u * (size_t)e.z;
                 const float4 f0 = pr[0], f1 = pr[1], m0 = pr[2], m1 = pr[3];
-                RngKey key;
-                key.seed = P.R.seed;
-                key.pixel = __float_as_uint(tl1.z);
-                key.sample = __float_as_uint(tl1.w);
-                const ShadeResult sr = shade_rec<QUADS>(scene, f0, f1, m0, m1, r, __uint_as_float(e.y), key, P.segment);
+                const ShadeResult sr =
+                    shade_rec<QUADS>(scene, f0, f1, m0, m1, r, __uint_as_float(e.y), key, P.segment, coop ? &unit : nullptr);
                 L = L + T * sr.emitted;
                 if (sr.scatters && P.segment < P.R.cam.max_depth) {
                     T = T * sr.attenuation;
