@@ -1247,6 +1247,10 @@ cudaError_t wavefront_render(WavefrontState* st, const RenderParams& p, bool cou
     if (B < 1u) return cudaErrorInvalidValue;
     const uint32_t n_batches = (p.sample_count + B - 1u) / B;
     int lanes_used = n_batches < (uint32_t)kLanes ? (int)n_batches : kLanes;
+    {   // RTB_WF_LANES_MAX=n caps the batches in flight (A/B measurements)
+        static const int cap = [] { const char* s = std::getenv("RTB_WF_LANES_MAX"); return s && s[0] ? std::atoi(s) : 0; }();
+        if (cap > 0 && lanes_used > cap) lanes_used = cap;
+    }
     for (int l = 0; l < lanes_used; ++l) {
         e = lane_reserve(&st->lanes[l], (size_t)B * slots_per_sample);
         if (e == cudaErrorMemoryAllocation && l > 0) {  // not enough memory for every lane: pipeline over fewer
