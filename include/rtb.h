@@ -246,8 +246,10 @@ enum {
      * test is CONSERVATIVE: it may enter a box an exact test would cull, never the reverse.  Leaves keep the
      * reference's f32 arithmetic, so t / p / normal of every hit are the same bits as in the other modes, and the set
      * of leaves tested is a superset of RTB_TRAVERSAL_SAH's.  Half the shared-memory traffic and 12 instead of 18
-     * issue slots per node visit.  Used when the packed layout fits in shared memory
-     * (<= 96 KB per octant, ~3 000 objects); larger scenes render exactly as RTB_TRAVERSAL_SAH. */
+     * issue slots per node visit.  The walk runs out of shared memory when one octant's packed
+     * layout fits (<= 96 KB, ~3 000 objects) and out of global memory otherwise (one 16-byte load per visit instead
+     * of two; binary16 planes over a large extent admit ~8 % more visits).  Environment: RTB_PACK_LARGE=0 renders
+     * scenes that do not fit shared memory exactly as RTB_TRAVERSAL_SAH (the behaviour before round 2's r3h). */
     RTB_TRAVERSAL_SAH16 = 3
 };
 
