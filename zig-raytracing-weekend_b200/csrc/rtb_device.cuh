@@ -250,9 +250,12 @@ struct DRay {
 // Camera.getRay (src/camera.zig:169-180) for flat pixel index (x = i % W + 1, y = i / W + 1,
 // 1-based: src/camera.zig:100-101).  Stream segment 0: block 0 = (jitter x, jitter y, time, -),
 // defocus-disk try j = block 1 + (j >> 1), words 2(j&1), 2(j&1)+1.
+__device__ __forceinline__ DRay get_ray(const DevCamera& cam, const RngKey& k, uint32_t x, uint32_t y);
 __device__ __forceinline__ DRay get_ray(const DevCamera& cam, const RngKey& k) {
-    const uint32_t x = k.pixel % cam.width + 1u;
-    const uint32_t y = k.pixel / cam.width + 1u;
+    return get_ray(cam, k, k.pixel % cam.width + 1u, k.pixel / cam.width + 1u);
+}
+// The same with the 1-based pixel coordinates supplied (a caller that already knows them saves two integer divisions).
+__device__ __forceinline__ DRay get_ray(const DevCamera& cam, const RngKey& k, uint32_t x, uint32_t y) {
     const float4 b0 = rng_block(k, 0u, 0u);
     const float3 pixel_center = cam.pixel00 + cam.du * splat3((float)x) + cam.dv * splat3((float)y);
     const float px = -0.5f + b0.x;

@@ -249,28 +249,35 @@ __global__ void __launch_bounds__(256) wf_raygen(const WfParams P) {
     const TimelineScope tl(P);
     const uint32_t total = P.slots_per_sample * P.batch_samples;
     const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t tiles_x = (P.R.cam.width + kTileW - 1u) / kTileW;
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
-        const uint32_t slot = base + threadIdx.x;
+        // slots_per_sample is a multiple of the 256 slots of a tile and so is `base`: the whole block is in ONE tile of ONE
+        // sample, and every integer division of slot -> (sample, tile, pixel) is block-uniform (seven per thread before).
+        const uint32_t sample = base / P.slots_per_sample;
+        const uint32_t tile = ((base - sample * P.slots_per_sample) / kCtaThreads) * P.R.tile_world + P.R.tile_rank;
+        const uint32_t tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        const uint32_t px = tile_x * kTileW + (warp & 3u) * 8u + (lane & 7u);
+        const uint32_t py = tile_y * kTileH + (warp >> 2) * 4u + (lane >> 3);
+        const uint32_t pixel = py * P.R.cam.width + px;  // == slot_pixel(P.R, slot % slots_per_sample, .)
+        const uint32_t slot = base + threadIdx.x;        // < total: total is a multiple of 256 too
         bool push = false;
         DRay ray;
         ray.o = ray.d = f3(0.f, 0.f, 0.f);
         ray.time = 0.f;
-        if (slot < total) {
-            uint32_t pixel;
-            if (slot_pixel(P.R, slot % P.slots_per_sample, pixel)) {
-                // the path's Philox key (pixel, sample) rides in the two spare words of its (T, L) record, so that
-                // wf_shade does not have to recompute it from the slot (four 32-bit integer divisions per hit)
-                const uint32_t sample = P.batch_begin + slot / P.slots_per_sample;
-                P.TL[2u * (size_t)slot] = make_float4(1.f, 1.f, 1.f, 0.f);
-                P.TL[2u * (size_t)slot + 1u] = make_float4(0.f, 0.f, __uint_as_float(pixel), __uint_as_float(sample));
-                if (P.R.cam.max_depth != 0u) {
-                    RngKey key;
-                    key.seed = P.R.seed;
-                    key.pixel = pixel;
-                    key.sample = sample;
-                    ray = get_ray(P.R.cam, key);
-                    push = true;
-                }
+        if (px < P.R.cam.width && py < P.R.cam.height && pixel >= P.R.pixel_begin && pixel < P.R.pixel_end) {
+            // the path's Philox key (pixel, sample) rides in the two spare words of its (T, L) record, so that
+            // wf_shade does not have to recompute it from the slot (four 32-bit integer divisions per hit)
+            const uint32_t sample_index = P.batch_begin + sample;
+            P.TL[2u * (size_t)slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+            P.TL[2u * (size_t)slot + 1u] = make_float4(0.f, 0.f, __uint_as_float(pixel), __uint_as_float(sample_index));
+            if (P.R.cam.max_depth != 0u) {
+                RngKey key;
+                key.seed = P.R.seed;
+                key.pixel = pixel;
+                key.sample = sample_index;
+                ray = get_ray(P.R.cam, key, px + 1u, py + 1u);
+                push = true;
             }
         }
         push_ray(P, ray, slot, push);
