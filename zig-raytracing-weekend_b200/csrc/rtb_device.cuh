@@ -733,7 +733,8 @@ __device__ __forceinline__ __half2 packed_interval(float t_min, float t_max, flo
 }
 
 // Walk over one octant's packed layout.  SMEM: `smem_base` is the shared-window address of the staged copy, whose skip
-// links are addresses (rewritten while staging); otherwise `slots` is the octant's array and the links are slot indices.
+// links are byte distances from the node that holds them (rewritten while staging); otherwise `slots` is the octant's
+// array and the links are slot indices.
 template <bool COUNT, bool QUADS, bool SMEM>
 __device__ __forceinline__ Nearest traverse_packed(const uint4* __restrict__ slots, ComplexTables quads,
                                                    float3 o, float3 d, float time, const PackedRay& pr, float t_min,
@@ -749,54 +750,60 @@ __device__ __forceinline__ Nearest traverse_packed(const uint4* __restrict__ slo
     __half2 K = packed_interval(t_min, t_max, pr.sigma);
     constexpr uint32_t kStep = SMEM ? 16u : 1u;
     uint32_t i = SMEM ? smem_base : 0u;
-    for (;;) {
-        uint4 n;
+    // Written as "walk box nodes until a leaf or the end, then handle it" with the node fetch at the BOTTOM of the inner
+    // loop, which is how the warp executes it anyway (the compiler reconverges at the leaf): one branch per visit
+    // instead of two.
+    auto fetch = [&](uint32_t at) {
+        uint4 v;
         if (SMEM) {
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(n.x), "=r"(n.y), "=r"(n.z), "=r"(n.w) : "r"(i));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at));
         } else {
-            n = slots[i];
+            v = slots[at];
         }
-        if (n.w < (1u << 30)) {  // box node: word 3 is the skip link
+        return v;
+    };
+    uint4 n = fetch(i);
+    for (;;) {
+        while (n.w < (1u << 30)) {  // box node: word 3 is the skip link
             if (COUNT) ++n_box;
             const __half2 tx = __hfma2(as_h2(n.x), ix, nx);
             const __half2 ty = __hfma2(as_h2(n.y), iy, ny);
             const __half2 tz = __hfma2(as_h2(n.z), iz, nz);
             const __half2 r = __hmax2(__hmax2(tx, ty), __hmax2(tz, K));  // (t_entry, -t_exit); NaN operands are ignored
             const bool miss = __hge(__high2half(r), __hneg(__low2half(r)));  // t_exit <= t_entry
-            i = miss ? n.w : i + kStep;
-        } else {
-            if (n.w == RTB_META_END) break;
-            if (COUNT) ++n_obj;
-            uint4 m;
-            if (SMEM) {
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(i));
-            } else {
-                m = slots[i + 1u];
-            }
-            const uint32_t kind = n.w >> 30;
-            bool hit;
-            float root;
-            if (!QUADS || kind != KIND_QUAD) {
-                const float3 c1 = f3(__uint_as_float(n.x), __uint_as_float(n.y), __uint_as_float(n.z));
-                const float3 cv = f3(__uint_as_float(m.x), __uint_as_float(m.y), __uint_as_float(m.z));
-                const float3 center = (kind == KIND_MOVING_SPHERE) ? c1 + splat3(time) * cv : c1;
-                // word 3 holds -radius (bit 31 marks a leaf's second slot); only radius^2 is used here
-                hit = sphere_root_a(o, d, a, center, __uint_as_float(m.w), t_min, best.t, root);
-            } else {
-                DRay r;
-                r.o = o;
-                r.d = d;
-                r.time = time;
-                const float4 f1 = make_float4(__uint_as_float(m.x), 0.0f, 0.0f, __uint_as_float(m.w & 0x7fffffffu));
-                hit = complex_root(r, quads, f1, t_min, best.t, root, key, segment, n.w & RTB_META_INDEX_MASK);
-            }
-            if (hit) {
-                best.t = root;
-                best.node = n.w & RTB_META_INDEX_MASK;
-                K = packed_interval(t_min, root, pr.sigma);
-            }
-            i = i + 2u * kStep;
+            // SMEM: the staged links are byte distances from the node itself, so the walk adds either the link or one
+            // slot to its address (SEL + IADD on a register that is not part of the fetched quad)
+            if (SMEM) i += miss ? n.w : kStep;
+            else      i = miss ? n.w : i + kStep;
+            n = fetch(i);
         }
+        if (n.w == RTB_META_END) break;
+        if (COUNT) ++n_obj;
+        const uint4 m = fetch(i + kStep);
+        const uint32_t kind = n.w >> 30;
+        bool hit;
+        float root;
+        if (!QUADS || kind != KIND_QUAD) {
+            const float3 c1 = f3(__uint_as_float(n.x), __uint_as_float(n.y), __uint_as_float(n.z));
+            const float3 cv = f3(__uint_as_float(m.x), __uint_as_float(m.y), __uint_as_float(m.z));
+            const float3 center = (kind == KIND_MOVING_SPHERE) ? c1 + splat3(time) * cv : c1;
+            // word 3 holds -radius (bit 31 marks a leaf's second slot); only radius^2 is used here
+            hit = sphere_root_a(o, d, a, center, __uint_as_float(m.w), t_min, best.t, root);
+        } else {
+            DRay r;
+            r.o = o;
+            r.d = d;
+            r.time = time;
+            const float4 f1 = make_float4(__uint_as_float(m.x), 0.0f, 0.0f, __uint_as_float(m.w & 0x7fffffffu));
+            hit = complex_root(r, quads, f1, t_min, best.t, root, key, segment, n.w & RTB_META_INDEX_MASK);
+        }
+        if (hit) {
+            best.t = root;
+            best.node = n.w & RTB_META_INDEX_MASK;
+            K = packed_interval(t_min, root, pr.sigma);
+        }
+        i = i + 2u * kStep;
+        n = fetch(i);
     }
     return best;
 }

@@ -345,8 +345,9 @@ wf_extend(const WfParams P) {
                 for (uint32_t i = threadIdx.x; i < (uint32_t)oct_stride; i += blockDim.x) {
                     float4 v = nodes[i];
                     const uint32_t meta = __float_as_uint(v.w);
-                    // every slot: word 3 < 2^30 <=> box node (leaves set bit 30/31 in both of their slots)
-                    if (meta < (1u << 30)) v.w = __uint_as_float(smem_base + meta * 16u);
+                    // every slot: word 3 < 2^30 <=> box node (leaves set bit 30/31 in both of their slots); the skip links
+                    // (slot indices) become byte distances from the node itself (see traverse_packed)
+                    if (meta < (1u << 30)) v.w = __uint_as_float((meta - i) * 16u);  // distance to the skip target in bytes
                     rtb_smem_nodes[i] = v;
                 }
             } else {  // a node becomes (entry, exit) pairs per axis for the packed-FP32 slab test (see traverse_octant)
@@ -460,7 +461,8 @@ __device__ __forceinline__ void extend_group(const WfParams& P, const uint4* __r
                 const __half2 tz = __hfma2(as_h2(n.z), iz, nz);
                 const __half2 r = __hmax2(__hmax2(tx, ty), __hmax2(tz, K));
                 const bool miss = __hge(__high2half(r), __hneg(__low2half(r)));
-                i = miss ? n.w : i + kStep;
+                if (SMEM) i += miss ? n.w : kStep;  // staged links are byte distances from the node (see traverse_packed)
+                else      i = miss ? n.w : i + kStep;
             }
             if (n.w == RTB_META_END) walking = false;
         }
@@ -572,7 +574,7 @@ wf_extend_evict(const WfParams P) {
                 for (uint32_t i = threadIdx.x; i < oct_stride; i += blockDim.x) {
                     float4 v = nodes[i];
                     const uint32_t meta = __float_as_uint(v.w);
-                    if (meta < (1u << 30)) v.w = __uint_as_float(smem_base + meta * 16u);
+                    if (meta < (1u << 30)) v.w = __uint_as_float((meta - i) * 16u);  // distance to the skip target in bytes
                     rtb_smem_nodes[i] = v;
                 }
                 __syncthreads();
