@@ -546,7 +546,7 @@ def run_ours(a):
                      "parity": "nearest-hit index, front_face, t, p, normal bit-exact against the oracle on every ray "
                                "(tests/test_gpu_parity.py::test_trace_*, test_full_frame_*)"}
 
-    # -- the other variants, one untimed-for-the-headline step each (evidence for the choice; device-resident) ----
+    # -- the other variants, one warmed-up step each (evidence for the choice; device-resident) ----
     variants = {}
     if not a.no_variants:
         for vint_name, vint in (("megakernel", p.RTB_INTEGRATOR_MEGAKERNEL), ("wavefront", p.RTB_INTEGRATOR_WAVEFRONT)):
@@ -555,6 +555,10 @@ def run_ours(a):
                 if a.scene == "million" and vtrav < 2:
                     continue    # the host's random-axis tree costs ~770 slab tests per ray there: seconds per sample
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                # one untimed render first: a mode's first render builds and uploads its layouts and learns the tail bounce
+                step_device(0, vint, spp=max(1, vspp // 4), trav=vtrav)
+                step_device(0, vint, spp=vspp, trav=vtrav)
+                torch.cuda.synchronize(dev)
                 e0.record(stream)
                 step_device(0, vint, spp=vspp, trav=vtrav)
                 e1.record(stream)
