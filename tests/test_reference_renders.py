@@ -9,11 +9,12 @@ frames cannot be reproduced pixel for pixel.  Above the horizon, though, they sh
   * the silhouettes of the three big spheres (src/main.zig:303-309; Sphere.hit, src/objects.zig) through the thin-lens
     camera (defocus 0.6, focus 10);
   * the upper cap of the metal sphere (albedo 0.7/0.6/0.5, fuzz 0): one mirror bounce into the sky
-    (Metal.scatter + vec3.reflect, src/material.zig).
+    (Metal.scatter + vec3.reflect, src/material.zig);
+  * the band of the glass sphere that shows the sky upside down (Dielectric.scatter, refract, Schlick), as block means.
 The same Book-1 scene (our seeded small spheres never rise above y = 0.4, i.e. stay below these rows) rendered by the
 oracle — and by the CUDA path — must reproduce those regions to within 8-bit rounding.  This is the independent anchor
-of the oracle for the camera / sphere / metal / colour pipeline; the traversal order, dielectric and lambertian
-statistics have no such anchor."""
+of the oracle for the camera / sphere / metal / dielectric / colour pipeline; the traversal order, lambertian
+statistics and textures have no such anchor."""
 import os
 
 import numpy as np
@@ -69,6 +70,14 @@ def _check_against_reference_render(img, ref, name):
     cap &= ~_dilate(~(m_img & m_ref), 3)
     assert cap.sum() > 9_000
     assert d[cap].max() <= 2, (name, d[cap].max())
+    # 4. inside the glass sphere, the band where it shows the sky upside down (rows 140..155; 8 x 8 blocks whose mean does
+    #    not depend on where the small spheres are — found by rendering three differently seeded scenes): two refractions
+    #    and the Schlick-weighted choice between reflecting and refracting (Dielectric.scatter, vec3.refract,
+    #    src/material.zig:80-117) reproduce the reference's block means to 8-bit rounding + sampling noise
+    for (y0, x0) in ((140, 324), (140, 332), (140, 356), (140, 364), (140, 372), (148, 364), (148, 372)):
+        got = img[y0:y0 + 8, x0:x0 + 8].reshape(-1, 3).mean(axis=0)
+        want = ref[y0:y0 + 8, x0:x0 + 8].reshape(-1, 3).mean(axis=0)
+        assert want[2] > 240 and np.abs(got - want).max() <= 2.5, (name, y0, x0, got, want)
     return float(iou), float(d[sky].mean()), int(d[cap].max())
 
 
