@@ -266,8 +266,8 @@ def parity_block(p, orc, np, scene, world, camo, integrator, traversal, parity_s
     threads = os.cpu_count() or 1
     out = {"integrator": "wavefront" if integrator == p.RTB_INTEGRATOR_WAVEFRONT else "megakernel",
            "traversal": TRAVERSALS[traversal], "oracle": "oracle/oracle.cpp — pinned on the reference's committed renders (sky, "
-           "sphere silhouettes, metal reflection, refracted sky in the glass sphere: tests/test_reference_renders.py) and its "
-           "AABB / UV / stb_image fixtures; traversal order, lambertian statistics and textures unpinned"}
+           "sphere silhouettes, metal reflection, refracted sky in the glass sphere, sky-lit lambertian sphere: tests/test_reference_renders.py) and its "
+           "AABB / UV / stb_image fixtures; BVH visiting order, textures, quads and media unpinned"}
     # (a) nearest-hit index on >= 1e5 camera + bounce rays
     rng = np.random.default_rng(99)
     n_cam = 70000

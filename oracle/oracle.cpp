@@ -1,5 +1,5 @@
 // oracle.cpp — CPU restatement of the reference's path-tracing hot path.  See oracle.h: TEST
-// INFRASTRUCTURE ONLY, pinned on the reference's committed renders for camera/sphere/metal/dielectric/colour, otherwise unpinned.  Build: g++ -std=c++17 -O2 -ffp-contract=off (Makefile).
+// INFRASTRUCTURE ONLY, pinned on the reference's committed renders for camera/spheres/materials/colour; visiting order, textures, quads, media unpinned.  Build: g++ -std=c++17 -O2 -ffp-contract=off (Makefile).
 //
 // Evaluation order of every float expression follows the Zig source (element-wise @Vector ops,
 // left-associative + and *), because decision arithmetic (slab test, discriminant, roots,

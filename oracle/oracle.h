@@ -10,10 +10,10 @@
  * here (no Zig toolchain, HEAD does not type-check, no headless mode — SURVEY.md §8c) and its
  * own tests pin none of the hot path's numbers.  The oracle is pinned against OUTPUTS OF THE REFERENCE
  * PROGRAM where they are deterministic — the sky, the big spheres' silhouettes, the metal sphere's sky
- * reflection and the refracted sky inside the glass sphere in the two renders the reference commits (image.png, image2.png ->
+ * reflection, the refracted sky inside the glass sphere and the sky-lit top of the lambertian sphere in the two renders the reference commits (image.png, image2.png ->
  * tests/golden/ref_renders_top160.npz, tests/test_reference_renders.py: equal to 8-bit rounding) —
- * which anchors Camera.init / getRay, Sphere.hit, Metal.scatter, Dielectric.scatter (as a statistic) and
- * the colour pipeline.  The BVH visiting order, lambertian statistics, textures, quads and media remain UNPINNED.
+ * which anchors Camera.init / getRay, Sphere.hit, Metal.scatter, Dielectric.scatter and Lambertian.scatter (as
+ * statistics) and the colour pipeline.  The BVH visiting order and tie rule, textures, quads and media remain UNPINNED.
  * Besides that it is pinned against the few known-answer vectors the reference source carries (the 3
  * AABB cases of the stale test at src/aabb.zig:117-136 and the UV table in the comment at
  * src/objects.zig:105-107, earthmap.jpg through the reference's own vendored stb_image) plus
