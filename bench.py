@@ -725,6 +725,9 @@ def run_ours(a):
                                  "object_tests": cst_act["n_object_tests"] / cst_act["n_paths"],
                                  "hits": cst_act["n_hits"] / cst_act["n_paths"]},
         "fp32": fp32_part, "hbm": hbm_part,
+        **({"note": "hbm frac > 1: SURVEY 8d's algorithmic node / primitive bytes are mostly served by L1 and L2 (the walk revisits "
+                    "the top of the tree); hbm.measured_dram_frac is the DRAM-side fraction, and the walk is bound by L2 "
+                    "latency, not by HBM bandwidth (DESIGN.md section 5, C4)"} if hbm_binds and bound["frac"] > 1.0 else {}),
         "work_per_path": {"rays": cst["n_rays"] / cst["n_paths"], "box_tests": cst["n_box_tests"] / cst["n_paths"],
                           "object_tests": cst["n_object_tests"] / cst["n_paths"], "hits": cst["n_hits"] / cst["n_paths"]},
     }
