@@ -24,7 +24,11 @@
 // remaining paths are finished by ONE launch of wf_tail instead of dozens of nearly empty kernel pairs.
 // Five dynamic-ray-fetch variants of the extend kernel (per-lane and thresholded refill, with and without
 // leaf batching / while-while, with a guard-free self-looping sentinel) were measured on B200 and all lost
-// to the plain one-thread-per-ray loop, so they are not kept.
+// to the plain one-thread-per-ray loop, so they are not kept.  Two later attempts at the idle lanes ARE
+// kept, off by default, because their images are bit-identical and their ncu counters are the evidence DESIGN.md §5.17
+// and §5.23 argue from: wf_extend_stream (lane refill + parked leaves) and wf_extend_evict (straggler eviction).
+// Batches of ~4 Mi paths are pipelined over eight streams ("lanes"), one wf_extend CTA per SM per launch, so that the
+// kernels of different batches — at different bounces — share every SM.
 #include "rtb_wavefront.cuh"
 
 #include <new>
