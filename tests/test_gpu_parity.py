@@ -320,14 +320,16 @@ def test_async_progress_and_cancel(pkg, book1):
     job.destroy()
 
 
-def test_statistical_parity_different_seeds(pkg, orc, book1):
-    """North-star image bar: RMSE(GPU,CPU) <= 1.25 RMSE_self, |mean bias| <= max(0.002, 3 RMSE_self/sqrt(WH))."""
+@pytest.mark.parametrize("integrator,traversal", [(0, 0), (1, 0), (1, 3)])
+def test_statistical_parity_different_seeds(pkg, orc, book1, integrator, traversal):
+    """North-star image bar: RMSE(GPU,CPU) <= 1.25 RMSE_self, |mean bias| <= max(0.002, 3 RMSE_self/sqrt(WH)) — for the
+    megakernel and the wavefront integrator in reference order and for the benchmarked mode (wavefront + SAH16)."""
     world, scene = book1
     spp = 32
     cam = pkg.book1_camera(240, spp, 50).init()
     c1 = orc.render(world.desc, cam, pkg.render_options(seed=4321), want_rgba=False)[0]
     c2 = orc.render(world.desc, cam, pkg.render_options(seed=8765), want_rgba=False)[0]
-    g = scene.render(cam, pkg.render_options(seed=1234))[0]
+    g = scene.render(cam, pkg.render_options(seed=1234, integrator=integrator, traversal=traversal))[0]
     m = lambda a: a[:, :3] / a[:, 3:4]
     rmse_self = np.sqrt(((m(c1) - m(c2)) ** 2).mean(axis=0))
     rmse = np.sqrt(((m(g) - m(c1)) ** 2).mean(axis=0))
