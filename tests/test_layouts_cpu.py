@@ -348,3 +348,44 @@ def test_python_walk_of_the_packed_layout_finds_the_oracle_hits(pkg, orc):
         if 150 + 60 <= k < 150 + 80:                                   # far origins: scaled to fit binary16, not dropped
             assert n_box <= n_box32 + 8, (k, n_box, n_box32)
     assert tot32 <= tot16 <= 1.08 * tot32                              # ... at a small price in extra visits
+
+
+def test_packed_layout_of_a_scene_too_large_for_shared_memory(pkg, orc):
+    """Since r3h the packed SAH16 layout is also built for scenes whose layout does not fit shared memory (it is then walked
+    from global memory).  Its binary16 planes then span a much larger extent relative to the objects: the Python model of
+    the device arithmetic must still find the oracle's hit for every ray (conservative), at a moderate price in visits."""
+    world = pkg.World.create(pkg.RTW_SCENE_RANDOM_SPHERES, n_spheres=6000)
+    S0, _, _ = _packed(pkg, world, 0)
+    assert S0.shape[0] * 16 > 96 * 1024                                # one octant does not fit the 96 KB staging limit
+    cam = pkg.million_camera(320, 4, 50).init()
+    rng = np.random.default_rng(11)
+    rays = orc.get_rays(cam, 3, rng.integers(0, cam.image_width * cam.image_height, 120), 0)
+    inside = np.zeros(120, dtype=rays.dtype)
+    inside["origin"] = rng.uniform(-30, 30, (120, 3)).astype(np.float32)
+    inside["origin"][:, 1] = rng.uniform(0.1, 5, 120).astype(np.float32)
+    inside["direction"] = rng.normal(size=(120, 3)).astype(np.float32)
+    inside["time"] = rng.random(120).astype(np.float32)
+    inside["t_min"], inside["t_max"] = 0.001, np.inf
+    rays = np.concatenate([rays, inside])
+    cpu = orc.trace_rays(world.desc, rays)
+    assert (cpu["object"] >= 0).mean() > 0.3
+    layouts = {}
+    f32_layouts = {}
+    tot16 = tot32 = 0
+    for k, ray in enumerate(rays):
+        bits = ray["direction"].view(np.uint32)
+        octant = sum((1 << a) for a in range(3) if int(bits[a]) >= 0x80000000 and int(bits[a]) - 0x80000000 < 0x7F800000)
+        if octant not in layouts:
+            layouts[octant] = _packed(pkg, world, octant)
+            f32_layouts[octant] = _layout(pkg, world, 2, octant)
+        S, center, scale = layouts[octant]
+        obj, t, n_box, n_obj = _walk_packed(S, center, scale, ray)
+        assert obj == cpu["object"][k], k
+        if obj >= 0:
+            assert np.float32(t) == cpu["t"][k]
+        L, n = f32_layouts[octant]
+        _, _, n_box32, n_obj32 = _walk(L, n, None, ray)
+        assert n_obj >= n_obj32
+        tot16 += n_box
+        tot32 += n_box32
+    assert tot32 <= tot16 <= 1.35 * tot32, (tot16, tot32)
