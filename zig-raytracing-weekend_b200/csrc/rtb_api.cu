@@ -868,7 +868,8 @@ extern "C" int rtb_scene_create(const RtbSceneDesc* desc, int device, RtbScene**
         }
         if (deepest > 1u) {
             size_t have = 0;
-            const size_t want = 1024u + 768u * (size_t)deepest;
+            // (generous: the kernels that walk a layout in global memory run at 32 registers and spill more per frame)
+            const size_t want = 2048u + 1024u * (size_t)deepest;
             if (cudaDeviceGetLimit(&have, cudaLimitStackSize) == cudaSuccess && have < want) {
                 const cudaError_t e = cudaDeviceSetLimit(cudaLimitStackSize, want);
                 if (e != cudaSuccess) {
