@@ -167,3 +167,65 @@ def test_instancing_zoo_render_parity(pkg, orc, integrator):
         assert np.count_nonzero(diff > tol) <= 6e-3 * diff.shape[0], (mode, np.count_nonzero(diff > tol))
         assert gs["n_paths"] == cs["n_paths"] and abs(gs["n_rays"] - cs["n_rays"]) <= 2e-3 * cs["n_rays"]
     assert c[:, :3].max() > 6.0     # the light inside the nested list is visible
+
+
+def _big_zoo(pkg, n_extra=4000):
+    """The zoo above plus thousands of small spheres: the layouts no longer fit shared memory, so the kernels that can test
+    complex leaves (QUADS) walk them from GLOBAL memory (32 registers per thread on that path, nested recursion on the
+    local-memory stack)."""
+    w = pkg.World.new()
+    rng = np.random.default_rng(77)
+    metal = pkg.material_spec(material=pkg.RTB_MAT_METAL, color=(0.8, 0.6, 0.2), fuzz=0.2)
+    glass = pkg.material_spec(material=pkg.RTB_MAT_DIELECTRIC, ir=1.5)
+    w.add_object(w.obj_translate(w.obj_sphere((0, 0, 0), 0.6, _grey(pkg), center2=(0.2, 0.1, 0)), (1.5, 0.5, -1.0)))
+    w.add_object(w.obj_rotate_y(w.obj_quad((-1, -1, 0), (2, 0, 0), (0, 2, 0), _grey(pkg, (0.2, 0.8, 0.3))), 35.0))
+    inner = w.obj_list([w.obj_sphere((0, 0, 0), 0.35, _grey(pkg, (0.9, 0.2, 0.2))), w.obj_box((0.4, -0.2, -0.2), (0.9, 0.3, 0.3), metal)])
+    w.add_object(w.obj_translate(w.obj_rotate_y(w.obj_translate(inner, (0.3, 0, 0)), -50.0), (0.5, -1.2, 1.0)))
+    w.add_object(w.obj_medium(w.obj_sphere((1.8, -0.8, 1.6), 0.8, glass), 1.5, (0.9, 0.9, 1.0)))
+    w.add_box((-2.5, -1.0, -2.5), (-1.5, 0.2, -1.6), _grey(pkg), angle=25.0, offset=(0.1, 0.0, 0.2))
+    for _ in range(n_extra):
+        c = rng.uniform(-9, 9, 3)
+        w.add_sphere(tuple(float(x) for x in c), float(rng.uniform(0.03, 0.12)), _grey(pkg, tuple(float(x) for x in rng.uniform(0.1, 0.9, 3))))
+    w.add_sphere((0, -101.5, 0), 100.0, _grey(pkg, (0.5, 0.5, 0.5)))
+    return w.build()
+
+
+@pytest.mark.gpu
+def test_complex_objects_on_the_global_memory_path(pkg, orc):
+    world = _big_zoo(pkg)
+    assert world.n_nodes * 32 > 96 * 1024          # one octant's layout does not fit the shared-memory staging limit
+    scene = pkg.Scene(world)
+    rng = np.random.default_rng(33)
+    rays = np.concatenate([_rays(pkg, rng, 20000, -8, 8), _rays(pkg, rng, 6000, -2.5, 2.5)])
+    cpu = orc.trace_rays(world.desc, rays)
+    d = world.desc.contents
+    is_medium = np.array([o >= 0 and d.hittables[o].type == pkg.RTB_HITTABLE_MEDIUM_OF for o in cpu["object"]])
+    # the host's tree construction reorders the top-level objects (like the reference's constructTree sorts its slice); the
+    # detached children of wrappers follow them
+    types = np.array([d.hittables[i].type for i in range(d.n_hittables)])
+    n_top = min(int(d.hittables[i].child) for i in range(d.n_hittables) if types[i] >= pkg.RTB_HITTABLE_TRANSLATE)
+    complex_tops = [i for i in range(n_top) if types[i] != pkg.RTB_HITTABLE_SPHERE]
+    assert len(complex_tops) == 5
+    hit_objects = set(cpu["object"][cpu["object"] >= 0].tolist())
+    assert set(complex_tops) <= hit_objects and is_medium.sum() > 200            # every complex object is hit by some ray
+    for mode in (0, 2, 3):
+        gpu = scene.trace_rays(rays, traversal=mode)
+        same = gpu["object"] == cpu["object"]
+        assert (~same).mean() < 2e-3, (mode, int((~same).sum()))
+        solid = (cpu["object"] >= 0) & same & ~is_medium
+        for k in ("front_face", "t", "p", "normal"):
+            assert np.array_equal(gpu[k][solid], cpu[k][solid]), (mode, k)
+    cam = pkg.Camera(image_width=160, aspect_ratio=1.0, samples_per_pixel=4, max_depth=20, vfov=60.0, lookfrom=(0.5, 1.0, 7.0),
+                     lookat=(0, 0, 0), defocus_angle=0.0, background=(0.6, 0.7, 0.9)).init()
+    ref = None
+    for integrator, mode in ((0, 0), (1, 0), (1, 3)):
+        o = pkg.render_options(seed=5, integrator=integrator, traversal=mode)
+        g, _, _ = scene.render(cam, o)
+        if ref is None:
+            c, _, _ = orc.render(world.desc, cam, o, n_threads=8)
+            ref = g
+        diff = np.abs(g[:, :3] - c[:, :3]).max(axis=1)
+        tol = 1e-4 * np.maximum(1.0, np.abs(c[:, :3]).max(axis=1))
+        assert np.count_nonzero(diff > tol) <= 1e-2 * diff.shape[0], (integrator, mode, np.count_nonzero(diff > tol))
+        if mode == 0:
+            assert np.array_equal(g, ref)            # megakernel == wavefront in reference order, bit for bit
