@@ -74,9 +74,6 @@ constexpr uint32_t kExtendThreads = RTB_EXTEND_THREADS;
 // 80 registers (3 CTAs, no spills) measured +2.5 % on Book-1 and +3.3 % on the textured scene, 64 registers +1 %,
 // 128 registers -13 % (profiles/r3b_shade_occ_ab.log, r3c_shade_occ_ab.log); likewise 5 instead of 8 CTAs per SM
 // in its grid (+1 %).
-#ifndef RTB_EXTEND_CONTIGUOUS
-#define RTB_EXTEND_CONTIGUOUS 1
-#endif
 // RTB_SHADE_COOP=1: wf_shade draws the random unit vectors of a lambertian / metal chunk warp-cooperatively
 // (random_unit_vector_coop: idle lanes evaluate the next tries of the paths whose rejection loop is still running).
 // Bit-identical; measured (profiles/r3m_coop_ab.log, r3n_coop_*.csv): 29 instead of 21-24 of 32 lanes per instruction
