@@ -111,6 +111,55 @@ int main(int argc, char** argv) {
         for (int j=0;j<3;++j) printf("%s k=%d: mean walk %.1f visits, longest in its warp %.1f, utilisation %.3f\n", rayfile, ks[j], sum[j]/ (mx[j]? 1:1) / (double)(rays.size()/32*32), mx[j]/(rays.size()/32), sum[j]/(32.0*mx[j]));
         return 0;
     }
+    if (scheme == 6) {
+        // PAIR visits: an interior node's two child boxes are tested in one visit (two independent
+        // chains behind one fetch), near child first (the per-octant layouts are already in near-first order), the far
+        // child on a per-lane stack; leaves are tested in phases like scheme 1.  Children of the box at i: A = i + 1 and
+        // B = skip link of A (pre-order); a box whose next entry is a leaf is that leaf's own box.
+        const int C_PAIR = argc > 4 ? atoi(argv[4]) : 25;
+        double pair_iters = 0, pair_lane = 0, boxtests = 0;
+        for (int oc=0;oc<8;++oc) for (size_t w=0; w+32<=q[oc].size(); w+=32) {
+            const std::vector<Node>& N = L[oc];
+            struct PL { Lane l; std::vector<uint32_t> st; int64_t pend; bool done; };
+            std::vector<PL> ln(32);
+            // the first entries are the huge objects' leaves (no box) and then the root's first subtree
+            uint32_t first = 0; while (fb(N[first].f[3]) >= (1u<<30) && fb(N[first].f[3]) != 0xffffffffu) ++first;
+            for (int t=0;t<32;++t){ Lane& l=ln[t].l; l.r=q[oc][w+t]; for(int k=0;k<3;++k) l.inv[k]=1.0f/l.r.d[k];
+                l.a=l.r.d[0]*l.r.d[0]+l.r.d[1]*l.r.d[1]+l.r.d[2]*l.r.d[2]; l.best=INFINITY; l.obj=-1; l.visits=l.leaves=0;
+                for (uint32_t h=0; h<first; ++h) { sphere(l, N[h]); }           // huge leaves: converged, cheap
+                ln[t].st.clear(); ln[t].pend=-1; ln[t].done=false;
+                // the two root subtrees: treated as the children of a virtual root
+                const uint32_t A=first, B=fb(N[first].f[3]);
+                bool hb = fb(N[B].f[3]) != 0xffffffffu && !slab_miss(N[B], l, l.best); bool ha = !slab_miss(N[A], l, l.best); boxtests+=2;
+                if (hb) ln[t].st.push_back(B); if (ha) ln[t].st.push_back(A);
+            }
+            nrays+=32; cost += 12;  // the huge leaves + virtual root, all lanes converged
+            for(;;){
+                bool any=false; for(int t=0;t<32;++t) if(!ln[t].done) any=true; if(!any) break;
+                outer++;
+                for(;;){ int act=0;
+                    for (int t=0;t<32;++t){ PL& p=ln[t]; if (p.done||p.pend>=0) continue;
+                        if (p.st.empty()) { p.done=true; continue; }
+                        ++act; const uint32_t i=p.st.back(); p.st.pop_back();   // a box already known to be hit when pushed
+                        // re-test against the current best (the pushed box may have been overtaken by a nearer hit)
+                        if (slab_miss(N[i], p.l, p.l.best)) { ++boxtests; continue; }
+                        const uint32_t m1=fb(N[i+1].f[3]);
+                        if (m1 >= (1u<<30)) { p.pend = i+1; continue; }        // i is a leaf's own box
+                        const uint32_t A=i+1, B=fb(N[A].f[3]);
+                        const bool ha=!slab_miss(N[A], p.l, p.l.best), hb=!slab_miss(N[B], p.l, p.l.best); boxtests+=2; ++p.l.visits;
+                        if (hb) p.st.push_back(B); if (ha) p.st.push_back(A);
+                    }
+                    if(!act) break; pair_iters++; pair_lane+=act; cost += C_PAIR; }
+                { int lc=-1, cnt=0; for(int t=0;t<32;++t){ PL& p=ln[t]; if (p.pend>=0){ ++cnt; ++p.l.leaves; lc=std::max(lc,sphere(p.l,N[p.pend])); p.pend=-1; } }
+                  if (lc>=0){ cost += (lc?C_LEAF1:C_LEAF0) + 4; leafphase++; leaflanes+=cnt; } }
+                cost += 6;
+            }
+            for(int t=0;t<32;++t){ visits+=ln[t].l.visits; leaves+=ln[t].l.leaves; }
+        }
+        printf("%s pair scheme: pair-visits/ray=%.2f box-tests/ray=%.2f leaves/ray=%.2f warp-instr/ray=%.1f (at %d per pair iteration) iters/warp=%.1f lanes/iter=%.1f leafphases/warp=%.1f\n",
+               rayfile, visits/nrays, boxtests/nrays, leaves/nrays, cost/nrays, C_PAIR, pair_iters/(nrays/32), pair_lane/pair_iters, leafphase/(nrays/32));
+        return 0;
+    }
     if (scheme == 4) {
         // while-while (K = 1) with STRAGGLER EVICTION: at a phase boundary (all lanes at a leaf or done) a warp with at
         // most T lanes still walking writes them to a continuation queue and ends; the stragglers of an octant are
